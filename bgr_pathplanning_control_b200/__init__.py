@@ -1,0 +1,20 @@
+"""bgr_pathplanning_control_b200 -- B200-native batched closed-loop rollout engine for the one data-parallel
+hot path of grimgrimberg/BGR_PathPlanning_Control (tracking law -> bicycle-model step -> lap metrics).
+
+Layout: ``csrc/`` sm_100a CUDA kernels + the C ABI (``include/bgr_rollout.h``);  ``_abi.py`` ctypes binding;
+``engine.py`` batched entry points;  ``controllers.py`` / ``car_state.py`` / ``metrics_calculator.py`` /
+``vehicle_config.py`` the host-side mirror of the reference's interface;  ``tracks.py`` / ``sweeps.py``
+synthetic inputs;  ``sharding.py`` multi-GPU plumbing;  ``roofline.py`` the frozen flop/byte counts.
+Importing the package does not load the CUDA library; the first call does and raises if it is not built.
+"""
+from . import _abi, tracks, sweeps, sharding, roofline          # noqa: F401
+from .vehicle_config import Vehicle_config, conf               # noqa: F401
+from .engine import (Track, RolloutConfig, RolloutResult, MpcConfig, MpcResult, rollout, mpc_evaluate,   # noqa: F401
+                     default_params, initial_states, candidate_bank, lqg_design, fp32_peak_probe,
+                     last_kernel_ms, launch_count)
+from .controllers import (PurePursuitController, StanleyController, AccelerationPIDController,            # noqa: F401
+                          LQGAccelerationController, MPCController, get_steering_controller,
+                          normalize_angle, find_target_point, compute_control_commands)
+from .car_state import State, States                            # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,1013 @@
+// The C ABI (include/bgr_rollout.h): argument checking, the track handle (derived tables, exactness
+// guards, cone candidate lists), kernel dispatch, host-buffer convenience entry points, LQG design and
+// the measurement helpers.  Nothing here computes a step on the CPU: without a CUDA device every compute
+// entry point returns BGR_ERR_CUDA.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "bgr_launch.cuh"
+#include "bgr_track.cuh"
+
+namespace bgr {
+
+static thread_local char g_error[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t err, const char* what) {
+  if (err == cudaSuccess) return BGR_OK;
+  set_error("%s: %s (%s)", what, cudaGetErrorString(err), cudaGetErrorName(err));
+  return BGR_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define BGR_CUDA(call)                                   \
+  do {                                                   \
+    int rc_ = ::bgr::check_cuda((call), #call);          \
+    if (rc_ != BGR_OK) return rc_;                       \
+  } while (0)
+
+// CUDA-event pair around the last hot kernel launched by this thread (bgr_last_kernel_ms)
+struct LastKernel {
+  cudaEvent_t start = nullptr, stop = nullptr;
+  int device = -1;
+  bool valid = false;
+};
+static thread_local LastKernel g_last;
+
+static int ensure_events(int device) {
+  if (g_last.start != nullptr && g_last.device == device) return BGR_OK;
+  if (g_last.start != nullptr) {
+    cudaEventDestroy(g_last.start);
+    cudaEventDestroy(g_last.stop);
+    g_last.start = g_last.stop = nullptr;
+  }
+  BGR_CUDA(cudaEventCreate(&g_last.start));
+  BGR_CUDA(cudaEventCreate(&g_last.stop));
+  g_last.device = device;
+  g_last.valid = false;
+  return BGR_OK;
+}
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int max_smem_optin = 0;
+};
+static int device_info(int device, DeviceInfo* out) {
+  static std::mutex mu;
+  static std::vector<DeviceInfo> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  if (static_cast<int>(cache.size()) <= device) cache.resize(device + 1);
+  if (cache[device].sm_count == 0) {
+    BGR_CUDA(cudaDeviceGetAttribute(&cache[device].sm_count, cudaDevAttrMultiProcessorCount, device));
+    BGR_CUDA(cudaDeviceGetAttribute(&cache[device].max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  }
+  *out = cache[device];
+  return BGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LQG design (host math): LQR gain of control.dlqr (core/controllers.py:97) by Riccati iteration and the
+// data-independent Kalman gain sequence (:145, :151, :154, :160).
+// ------------------------------------------------------------------------------------------------
+static void lqr_gain_host(double dt, double K[2]) {
+  // A = [[1,0],[dt,1]], B = [dt,0]^T, Q = diag(10,100), R = 0.001   (:83-94)
+  const long double a10 = dt, b0 = dt, q0 = 10.0L, q1 = 100.0L, R = 0.001L;
+  long double p00 = q0, p01 = 0, p11 = q1;  // symmetric P
+  long double k0 = 0, k1 = 0;
+  for (int it = 0; it < 200000; ++it) {
+    // PA = P A ; A = [[1,0],[a10,1]]
+    const long double pa00 = p00 + p01 * a10, pa01 = p01, pa10 = p01 + p11 * a10, pa11 = p11;
+    // BtPA = B^T P A = b0 * row0(PA)
+    const long double s = R + b0 * p00 * b0;
+    const long double g0 = b0 * pa00, g1 = b0 * pa01;
+    k0 = g0 / s;
+    k1 = g1 / s;
+    // AtPA = A^T (P A)
+    const long double m00 = pa00 + a10 * pa10, m01 = pa01 + a10 * pa11, m11 = pa11;
+    const long double n00 = m00 - g0 * k0 + q0, n01 = m01 - g0 * k1, n11 = m11 - g1 * k1 + q1;
+    const long double diff = fabsl(n00 - p00) + fabsl(n01 - p01) + fabsl(n11 - p11);
+    p00 = n00; p01 = n01; p11 = n11;
+    if (diff <= 1e-19L * (fabsl(p00) + fabsl(p11))) break;
+  }
+  K[0] = static_cast<double>(k0);
+  K[1] = static_cast<double>(k1);
+}
+
+static void kalman_gains_host(double dt, int n_steps, double* out /*[n][2]*/) {
+  // A = [[1,0],[dt,1]], C = [1,0], Q_kf = 0.1 I, R_kf = 0.5, P0 = I   (:83-87, :101-109)
+  double p00 = 1.0, p01 = 0.0, p10 = 0.0, p11 = 1.0;
+  for (int k = 0; k < n_steps; ++k) {
+    // AP = A P
+    const double ap00 = p00, ap01 = p01, ap10 = dt * p00 + p10, ap11 = dt * p01 + p11;
+    // P_pred = AP A^T + Q_kf ; A^T = [[1,dt],[0,1]]
+    const double pp00 = ap00 + 0.1, pp01 = ap00 * dt + ap01, pp10 = ap10, pp11 = ap10 * dt + ap11 + 0.1;
+    const double S = pp00 + 0.5;                 // :151
+    const double k0 = pp00 / S, k1 = pp10 / S;   // :154  P_pred C^T S^-1
+    // P = (I - K C) P_pred                       // :160
+    p00 = (1.0 - k0) * pp00;
+    p01 = (1.0 - k0) * pp01;
+    p10 = -k1 * pp00 + pp10;
+    p11 = -k1 * pp01 + pp11;
+    out[2 * k] = k0;
+    out[2 * k + 1] = k1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exactness guard of the local nearest-waypoint search.
+//
+// The kernels find the nearest waypoint by descending from the previous step's answer until both index
+// neighbours are no closer, i.e. until the car position p lies in the slab
+//   slab(j) = { p : |p - w_j| <= |p - w_{j-1}|  and  |p - w_j| <= |p - w_{j+1}| }.
+// j is the GLOBAL argmin unless some other waypoint i is closer, i.e. unless p is in the half plane
+//   H_i = { p : |p - w_i| <= |p - w_j| }.
+// guard(j) = min over i not in {j-1, j, j+1} of dist(w_j, slab(j) /\ H_i): every p of slab(j) with
+// |p - w_j| < guard(j) has j as its exact global argmin.  w_j is in slab(j) but not in H_i, so the point
+// of slab(j) /\ H_i nearest to w_j lies on the bisector line of (w_i, w_j) restricted to the slab:
+// a 1-D interval problem.  O(n^2) on the host, once per track.
+// ------------------------------------------------------------------------------------------------
+static void compute_guards(const std::vector<double>& x, const std::vector<double>& y, bool closed,
+                           std::vector<double>* guard) {
+  const int n = static_cast<int>(x.size());
+  guard->assign(n, 0.0);
+  for (int j = 0; j < n; ++j) {
+    int nb[2];
+    int n_nb = 0;
+    if (closed) {
+      nb[n_nb++] = (j + n - 1) % n;
+      nb[n_nb++] = (j + 1) % n;
+    } else {
+      if (j > 0) nb[n_nb++] = j - 1;
+      if (j < n - 1) nb[n_nb++] = j + 1;
+    }
+    double ex[2], ey[2], eh[2];
+    bool degenerate = false;
+    for (int s = 0; s < n_nb; ++s) {
+      ex[s] = x[nb[s]] - x[j];
+      ey[s] = y[nb[s]] - y[j];
+      eh[s] = 0.5 * (ex[s] * ex[s] + ey[s] * ey[s]);
+      if (eh[s] == 0.0) degenerate = true;  // repeated waypoint: the descent cannot step over it
+    }
+    double best2 = INFINITY;
+    if (degenerate) best2 = 0.0;
+    for (int i = 0; i < n && best2 > 0.0; ++i) {
+      if (i == j || (n_nb > 0 && i == nb[0]) || (n_nb > 1 && i == nb[1])) continue;
+      const double wx = x[i] - x[j], wy = y[i] - y[j];
+      const double D2 = wx * wx + wy * wy;
+      if (D2 == 0.0) {  // coincident with a non-neighbour: only the exact scan can apply the index tie rule
+        best2 = 0.0;
+        break;
+      }
+      if (0.25 * D2 >= best2) continue;
+      const double D = std::sqrt(D2);
+      // bisector: q(t) = m + t u, m - w_j = (wx, wy) / 2, u = (-wy, wx) / D
+      const double ux = -wy / D, uy = wx / D;
+      double lo = -INFINITY, hi = INFINITY;
+      bool empty = false;
+      for (int s = 0; s < n_nb; ++s) {
+        // (q - w_j) . e_s <= |e_s|^2 / 2   <=>   t (u . e_s) <= |e_s|^2 / 2 - (m - w_j) . e_s
+        const double a = ux * ex[s] + uy * ey[s];
+        const double b = eh[s] - 0.5 * (wx * ex[s] + wy * ey[s]);
+        if (a > 0.0) hi = std::min(hi, b / a);
+        else if (a < 0.0) lo = std::max(lo, b / a);
+        else if (b < 0.0) empty = true;
+      }
+      if (empty || lo > hi) continue;
+      double t = 0.0;
+      if (lo > 0.0) t = lo;
+      else if (hi < 0.0) t = hi;
+      best2 = std::min(best2, 0.25 * D2 + t * t);
+    }
+    (*guard)[j] = std::sqrt(best2);  // may be +inf (e.g. a straight line)
+  }
+}
+
+}  // namespace bgr
+
+using namespace bgr;
+
+// ================================================================================================
+// library
+// ================================================================================================
+extern "C" int bgr_abi_version(void) { return BGR_ABI_VERSION; }
+
+extern "C" const char* bgr_last_error_string(void) { return g_error; }
+
+extern "C" int bgr_device_count(int* out_count) {
+  if (out_count == nullptr) {
+    set_error("bgr_device_count: out_count is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  *out_count = 0;
+  BGR_CUDA(cudaGetDeviceCount(out_count));
+  return BGR_OK;
+}
+
+extern "C" int64_t bgr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int bgr_last_kernel_ms(double* out_ms) {
+  if (out_ms == nullptr) {
+    set_error("bgr_last_kernel_ms: out_ms is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  if (!g_last.valid) {
+    set_error("bgr_last_kernel_ms: no kernel has been launched by this thread");
+    return BGR_ERR_BAD_ARG;
+  }
+  BGR_CUDA(cudaEventSynchronize(g_last.stop));
+  float ms = 0.0f;
+  BGR_CUDA(cudaEventElapsedTime(&ms, g_last.start, g_last.stop));
+  *out_ms = static_cast<double>(ms);
+  return BGR_OK;
+}
+
+extern "C" int bgr_lqg_design(double dt, int32_t n_steps, double* h_lqr_gain, double* h_kf_gains) {
+  if (!(dt > 0.0) || n_steps < 0 || h_lqr_gain == nullptr) {
+    set_error("bgr_lqg_design: need dt > 0, n_steps >= 0, h_lqr_gain != NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  lqr_gain_host(dt, h_lqr_gain);
+  if (h_kf_gains != nullptr && n_steps > 0) kalman_gains_host(dt, n_steps, h_kf_gains);
+  return BGR_OK;
+}
+
+// ================================================================================================
+// track handle
+// ================================================================================================
+template <typename T>
+static int upload(T** dst, const std::vector<T>& src) {
+  *dst = nullptr;
+  if (src.empty()) return BGR_OK;
+  BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), src.size() * sizeof(T)));
+  BGR_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return BGR_OK;
+}
+
+extern "C" void bgr_track_destroy(bgr_track_t* t) {
+  if (t == nullptr) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(t->device);
+  cudaFree(t->xy_f);
+  cudaFree(t->attr_f);
+  cudaFree(t->xy_d);
+  cudaFree(t->attr_d);
+  cudaFree(t->guard2);
+  cudaFree(t->cone_range);
+  cudaFree(t->cone_list);
+  cudaFree(t->cones);
+  cudaSetDevice(prev);
+  delete t;
+}
+
+extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_track_t** out_track) {
+  if (out_track == nullptr) {
+    set_error("bgr_track_create: out_track is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  *out_track = nullptr;
+  if (desc == nullptr || desc->h_x == nullptr || desc->h_y == nullptr || desc->h_kappa == nullptr) {
+    set_error("bgr_track_create: desc / h_x / h_y / h_kappa is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  const int n = desc->n;
+  if (n < 2 || (desc->closed && n < 3)) {
+    set_error("bgr_track_create: need n >= 2 waypoints (>= 3 when closed), got %d", n);
+    return BGR_ERR_BAD_ARG;
+  }
+  if (desc->n_cones < 0 || desc->n_cones > BGR_MAX_CONES || (desc->n_cones > 0 && desc->h_cones_xy == nullptr)) {
+    set_error("bgr_track_create: n_cones must be in [0, %d] with h_cones_xy set, got %d", BGR_MAX_CONES,
+              desc->n_cones);
+    return BGR_ERR_BAD_ARG;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (!std::isfinite(desc->h_x[i]) || !std::isfinite(desc->h_y[i]) || !std::isfinite(desc->h_kappa[i])) {
+      set_error("bgr_track_create: non-finite waypoint %d", i);
+      return BGR_ERR_BAD_ARG;
+    }
+  }
+  int n_dev = 0;
+  BGR_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) {
+    set_error("bgr_track_create: device %d out of range (%d CUDA devices)", device, n_dev);
+    return BGR_ERR_BAD_ARG;
+  }
+  DeviceInfo di;
+  int rc = device_info(device, &di);
+  if (rc != BGR_OK) return rc;
+  const int n_pad = (n + 3) & ~3;
+  if (rollout_smem_bytes<float>(n_pad) > static_cast<size_t>(di.max_smem_optin)) {
+    set_error("bgr_track_create: %d waypoints need %zu B of shared memory per CTA, device offers %d", n,
+              rollout_smem_bytes<float>(n_pad), di.max_smem_optin);
+    return BGR_ERR_TOO_LARGE;
+  }
+
+  bgr_track* t = new (std::nothrow) bgr_track();
+  if (t == nullptr) {
+    set_error("bgr_track_create: out of host memory");
+    return BGR_ERR_ALLOC;
+  }
+  t->device = device;
+  t->n = n;
+  t->n_pad = n_pad;
+  t->closed = desc->closed ? 1 : 0;
+  t->n_cones = desc->n_cones;
+  t->cone_reach = desc->cone_reach;
+  t->x.assign(desc->h_x, desc->h_x + n);
+  t->y.assign(desc->h_y, desc->h_y + n);
+  t->kappa.assign(desc->h_kappa, desc->h_kappa + n);
+
+  // path heading: forward difference, backward at the last index (core/controllers.py:361-368) --
+  // no wrap-around even on a closed lap, exactly like the reference
+  t->path_yaw.resize(n);
+  for (int j = 0; j < n; ++j) {
+    double dx, dy;
+    if (j < n - 1) {
+      dx = t->x[j + 1] - t->x[j];
+      dy = t->y[j + 1] - t->y[j];
+    } else {
+      dx = t->x[j] - t->x[j - 1];
+      dy = t->y[j] - t->y[j - 1];
+    }
+    t->path_yaw[j] = std::atan2(dy, dx);
+  }
+  compute_guards(t->x, t->y, t->closed != 0, &t->guard_radius);
+
+  t->ds_min = INFINITY;
+  t->ds_max = 0.0;
+  const int n_seg = t->closed ? n : n - 1;
+  for (int j = 0; j < n_seg; ++j) {
+    const int k = (j + 1) % n;
+    const double ds = std::hypot(t->x[k] - t->x[j], t->y[k] - t->y[j]);
+    t->ds_min = std::min(t->ds_min, ds);
+    t->ds_max = std::max(t->ds_max, ds);
+  }
+  {
+    std::vector<double> g = t->guard_radius;
+    std::sort(g.begin(), g.end());
+    t->guard_min = g.front();
+    t->guard_median = g[g.size() / 2];
+  }
+
+  std::vector<float2> xy_f(n_pad);
+  std::vector<float4> attr_f(n_pad);
+  std::vector<double2> xy_d(n_pad);
+  std::vector<D4> attr_d(n_pad);
+  std::vector<float> guard2(n_pad);
+  for (int j = 0; j < n_pad; ++j) {
+    const int s = std::min(j, n - 1);
+    const double sn = std::sin(t->path_yaw[s]), cs = std::cos(t->path_yaw[s]);
+    xy_d[j] = make_double2(t->x[s], t->y[s]);
+    attr_d[j] = D4{t->kappa[s], t->path_yaw[s], sn, cs};
+    xy_f[j] = make_float2(static_cast<float>(t->x[s]), static_cast<float>(t->y[s]));
+    attr_f[j] = make_float4(static_cast<float>(t->kappa[s]), static_cast<float>(t->path_yaw[s]),
+                            static_cast<float>(sn), static_cast<float>(cs));
+    // shrink by 1e-4 relative + 1e-4 m: the in-slab test itself runs in fp32 on rounded waypoints
+    double g = t->guard_radius[s];
+    g = std::isfinite(g) ? std::max(0.0, g * (1.0 - 1e-4) - 1e-4) : 1e18;
+    guard2[j] = static_cast<float>(std::min(g * g, 1e30));
+  }
+
+  // cone candidate lists: cones within cone_reach of waypoint j
+  std::vector<int32_t> cone_range(n, 0), cone_list;
+  std::vector<double2> cones(t->n_cones);
+  for (int c = 0; c < t->n_cones; ++c) cones[c] = make_double2(desc->h_cones_xy[2 * c], desc->h_cones_xy[2 * c + 1]);
+  if (t->n_cones > 0) {
+    for (int j = 0; j < n; ++j) {
+      const int first = static_cast<int>(cone_list.size());
+      int cnt = 0;
+      for (int c = 0; c < t->n_cones; ++c) {
+        if (std::hypot(cones[c].x - t->x[j], cones[c].y - t->y[j]) <= desc->cone_reach) {
+          cone_list.push_back(c);
+          ++cnt;
+        }
+      }
+      if (first >= (1 << 21)) {
+        delete t;
+        set_error("bgr_track_create: cone candidate lists overflow (cone_reach %.3f too large)", desc->cone_reach);
+        return BGR_ERR_TOO_LARGE;
+      }
+      cone_range[j] = (first << 10) | cnt;  // cnt <= BGR_MAX_CONES = 512 < 1024
+    }
+    if (cone_list.empty()) cone_list.push_back(0);
+  }
+
+  int prev = 0;
+  cudaGetDevice(&prev);
+  rc = check_cuda(cudaSetDevice(device), "cudaSetDevice");
+  if (rc == BGR_OK) rc = upload(&t->xy_f, xy_f);
+  if (rc == BGR_OK) rc = upload(&t->attr_f, attr_f);
+  if (rc == BGR_OK) rc = upload(&t->xy_d, xy_d);
+  if (rc == BGR_OK) rc = upload(&t->attr_d, attr_d);
+  if (rc == BGR_OK) rc = upload(&t->guard2, guard2);
+  if (rc == BGR_OK && t->n_cones > 0) {
+    rc = upload(&t->cone_range, cone_range);
+    if (rc == BGR_OK) rc = upload(&t->cone_list, cone_list);
+    if (rc == BGR_OK) rc = upload(&t->cones, cones);
+  }
+  cudaSetDevice(prev);
+  if (rc != BGR_OK) {
+    bgr_track_destroy(t);
+    return rc;
+  }
+  *out_track = t;
+  return BGR_OK;
+}
+
+extern "C" int bgr_track_info(const bgr_track_t* t, bgr_track_info_t* out) {
+  if (t == nullptr || out == nullptr) {
+    set_error("bgr_track_info: NULL argument");
+    return BGR_ERR_BAD_ARG;
+  }
+  out->n = t->n;
+  out->closed = t->closed;
+  out->n_cones = t->n_cones;
+  out->device = t->device;
+  out->smem_bytes_fp32 = static_cast<int64_t>(rollout_smem_bytes<float>(t->n_pad));
+  out->smem_bytes_fp64 = static_cast<int64_t>(rollout_smem_bytes<double>(t->n_pad));
+  out->guard_min = t->guard_min;
+  out->guard_median = t->guard_median;
+  out->ds_min = t->ds_min;
+  out->ds_max = t->ds_max;
+  return BGR_OK;
+}
+
+extern "C" int bgr_track_tables(const bgr_track_t* t, double* h_path_yaw, double* h_guard_radius) {
+  if (t == nullptr) {
+    set_error("bgr_track_tables: track is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  if (h_path_yaw != nullptr) std::copy(t->path_yaw.begin(), t->path_yaw.end(), h_path_yaw);
+  if (h_guard_radius != nullptr) std::copy(t->guard_radius.begin(), t->guard_radius.end(), h_guard_radius);
+  return BGR_OK;
+}
+
+// ================================================================================================
+// rollout
+// ================================================================================================
+namespace {
+
+struct StepPlumbing {
+  int32_t phases = BGR_PHASE_STEER | BGR_PHASE_ACCEL | BGR_PHASE_MODEL | BGR_PHASE_ERRORS;
+  const double* ctrl_in = nullptr;
+  double* ctrl_out = nullptr;
+  const int32_t* ti_in = nullptr;
+  int32_t* ti_out = nullptr;
+  double* state_out = nullptr;
+  const double* cmd = nullptr;
+  double* step_out = nullptr;
+  bool force_full = false;
+};
+
+using LaunchFn = cudaError_t (*)(const RolloutArgs&, int, size_t, cudaStream_t);
+
+template <typename Real, bool EXTRAS>
+LaunchFn pick(int s, int a, int m) {
+  const int key = s * 4 + a * 2 + m;
+  switch (key) {
+    case 0: return launch_rollout<Real, 0, 0, 0, EXTRAS>;
+    case 1: return launch_rollout<Real, 0, 0, 1, EXTRAS>;
+    case 2: return launch_rollout<Real, 0, 1, 0, EXTRAS>;
+    case 3: return launch_rollout<Real, 0, 1, 1, EXTRAS>;
+    case 4: return launch_rollout<Real, 1, 0, 0, EXTRAS>;
+    case 5: return launch_rollout<Real, 1, 0, 1, EXTRAS>;
+    case 6: return launch_rollout<Real, 1, 1, 0, EXTRAS>;
+    default: return launch_rollout<Real, 1, 1, 1, EXTRAS>;
+  }
+}
+
+int validate_cfg(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const char* who) {
+  if (track == nullptr || cfg == nullptr) {
+    set_error("%s: track / cfg is NULL", who);
+    return BGR_ERR_BAD_ARG;
+  }
+  if (cfg->steer_kind < 0 || cfg->steer_kind > 1 || cfg->accel_kind < 0 || cfg->accel_kind > 1 ||
+      cfg->model_kind < 0 || cfg->model_kind > 1 || cfg->precision < 0 || cfg->precision > 1) {
+    set_error("%s: unknown steer/accel/model/precision selector (%d, %d, %d, %d)", who, cfg->steer_kind,
+              cfg->accel_kind, cfg->model_kind, cfg->precision);
+    return BGR_ERR_BAD_ARG;
+  }
+  if (cfg->max_steps < 1 || cfg->laps < 1 || cfg->laps_target < 0 || !(cfg->dt > 0.0) || !(cfg->wheelbase > 0.0) ||
+      !(cfg->max_steer > 0.0) || !(cfg->max_accel >= cfg->max_decel) || cfg->hit_radius < 0.0 ||
+      cfg->tie_eps < 0.0 || cfg->sigma_xy < 0.0 || cfg->sigma_yaw < 0.0 || cfg->sigma_v < 0.0 ||
+      cfg->sigma_cone < 0.0) {
+    set_error("%s: invalid cfg (max_steps %d, laps %d, laps_target %d, dt %g, wheelbase %g, max_steer %g, ...)",
+              who, cfg->max_steps, cfg->laps, cfg->laps_target, cfg->dt, cfg->wheelbase, cfg->max_steer);
+    return BGR_ERR_BAD_ARG;
+  }
+  if (static_cast<long long>(track->n) * cfg->laps > 0x3fffffffLL) {
+    set_error("%s: n * laps overflows the target index", who);
+    return BGR_ERR_BAD_ARG;
+  }
+  if (cfg->hit_radius > 0.0 && track->n_cones > 0) {
+    const double need = cfg->hit_radius + 6.0 * cfg->sigma_cone + BGR_CONE_GUARD;
+    if (track->cone_reach < need) {
+      set_error("%s: track cone_reach %.3f < hit_radius + 6 sigma_cone + BGR_CONE_GUARD = %.3f", who,
+                track->cone_reach, need);
+      return BGR_ERR_BAD_ARG;
+    }
+  }
+  return BGR_OK;
+}
+
+int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes, const float* d_params,
+                 const double* d_init, float* d_metrics, int32_t* d_status, double* d_traj, double* d_aggregate,
+                 const StepPlumbing& sp, cudaStream_t stream) {
+  int rc = validate_cfg(track, cfg, "bgr_rollout");
+  if (rc != BGR_OK) return rc;
+  if (n_episodes < 0 || n_episodes > (1LL << 31) * kRolloutThreads) {
+    set_error("bgr_rollout: n_episodes %lld out of range", static_cast<long long>(n_episodes));
+    return BGR_ERR_BAD_ARG;
+  }
+  if (n_episodes == 0) {
+    if (d_aggregate != nullptr) {
+      double zero[BGR_N_AGG] = {0, 0, 0, 0, 0, 1e300, 0, 0};
+      BGR_CUDA(cudaMemcpyAsync(d_aggregate, zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+      BGR_CUDA(cudaStreamSynchronize(stream));
+    }
+    return BGR_OK;
+  }
+  if (d_params == nullptr || d_init == nullptr || d_metrics == nullptr || d_status == nullptr) {
+    set_error("bgr_rollout: d_params / d_init_state / d_metrics / d_status is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(d_params) & 15) || (reinterpret_cast<uintptr_t>(d_metrics) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_init) & 7)) {
+    set_error("bgr_rollout: d_params and d_metrics must be 16-byte aligned, d_init_state 8-byte aligned");
+    return BGR_ERR_BAD_ARG;
+  }
+
+  int prev = 0;
+  cudaGetDevice(&prev);
+  struct Restore {
+    int dev;
+    ~Restore() { cudaSetDevice(dev); }
+  } restore{prev};
+  BGR_CUDA(cudaSetDevice(track->device));
+  DeviceInfo di;
+  rc = device_info(track->device, &di);
+  if (rc != BGR_OK) return rc;
+
+  const bool f64 = cfg->precision == BGR_PRECISION_FP64;
+  const bool cones_on = cfg->hit_radius > 0.0 && track->n_cones > 0;
+  const bool noise_on = cfg->sigma_xy > 0.0 || cfg->sigma_yaw > 0.0 || cfg->sigma_v > 0.0;
+  const bool full = f64 || cones_on || noise_on || d_traj != nullptr || (cfg->flags & BGR_CFG_AUDIT) || sp.force_full;
+
+  const size_t smem = f64 ? rollout_smem_bytes<double>(track->n_pad) : rollout_smem_bytes<float>(track->n_pad);
+  if (smem > static_cast<size_t>(di.max_smem_optin)) {
+    set_error("bgr_rollout: track needs %zu B of shared memory per CTA in this precision, device offers %d", smem,
+              di.max_smem_optin);
+    return BGR_ERR_TOO_LARGE;
+  }
+
+  RolloutArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.trk = track->view();
+  A.params = d_params;
+  A.init = d_init;
+  A.metrics = d_metrics;
+  A.status = d_status;
+  A.traj = d_traj;
+  A.n_episodes = n_episodes;
+  A.episode_id_base = cfg->episode_id_base;
+  A.max_steps = cfg->max_steps;
+  A.laps = cfg->laps;
+  A.laps_target = cfg->laps_target;
+  A.n_total = cfg->steer_kind == BGR_STEER_PURE_PURSUIT ? track->n * cfg->laps : track->n;
+  A.dt = cfg->dt;
+  A.wheelbase = cfg->wheelbase;
+  A.l_f = cfg->l_f;
+  A.l_r = cfg->l_r;
+  A.max_steer = cfg->max_steer;
+  A.max_accel = cfg->max_accel;
+  A.max_decel = cfg->max_decel;
+  A.hit_radius = cfg->hit_radius;
+  A.tie_eps = cfg->tie_eps > 0.0 ? cfg->tie_eps : 2e-5;
+  A.sigma_xy = cfg->sigma_xy;
+  A.sigma_yaw = cfg->sigma_yaw;
+  A.sigma_v = cfg->sigma_v;
+  A.sigma_cone = cfg->sigma_cone;
+  A.seed = cfg->noise_seed;
+  A.cones_on = cones_on ? 1 : 0;
+  A.noise_on = noise_on ? 1 : 0;
+  A.phases = sp.phases;
+  A.ctrl_in = sp.ctrl_in;
+  A.ctrl_out = sp.ctrl_out;
+  A.ti_in = sp.ti_in;
+  A.ti_out = sp.ti_out;
+  A.state_out = sp.state_out;
+  A.cmd = sp.cmd;
+  A.step_out = sp.step_out;
+
+  const int grid = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
+
+  // LQG: LQR gain + the shared Kalman gain sequence
+  double* d_kf = nullptr;
+  if (cfg->accel_kind == BGR_ACCEL_LQG) {
+    double K[2];
+    lqr_gain_host(cfg->dt, K);
+    A.lqr_k0 = K[0];
+    A.lqr_k1 = K[1];
+    int kf_len = cfg->max_steps;
+    if (sp.ctrl_in != nullptr) kf_len = 4096;  // single-step API: index carried by the caller, clamped in-kernel
+    std::vector<double> gains(static_cast<size_t>(kf_len) * 2);
+    kalman_gains_host(cfg->dt, kf_len, gains.data());
+    BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_kf), gains.size() * sizeof(double), stream));
+    BGR_CUDA(cudaMemcpyAsync(d_kf, gains.data(), gains.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    BGR_CUDA(cudaStreamSynchronize(stream));  // `gains` is pageable host memory that dies with this scope
+    A.kf_gain = d_kf;
+    A.kf_len = kf_len;
+  }
+  double* d_partials = nullptr;
+  if (d_aggregate != nullptr) {
+    BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_partials), static_cast<size_t>(grid) * BGR_N_AGG * sizeof(double),
+                             stream));
+    A.block_partials = d_partials;
+  }
+
+  LaunchFn fn;
+  if (f64) fn = pick<double, true>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
+  else if (full) fn = pick<float, true>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
+  else fn = pick<float, false>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
+
+  rc = ensure_events(track->device);
+  if (rc != BGR_OK) return rc;
+  BGR_CUDA(cudaEventRecord(g_last.start, stream));
+  cudaError_t err = fn(A, grid, smem, stream);
+  if (err == cudaSuccess) {
+    count_launch();
+    BGR_CUDA(cudaEventRecord(g_last.stop, stream));
+    g_last.valid = true;
+    if (d_partials != nullptr) {
+      err = launch_reduce_partials(d_partials, grid, d_aggregate, stream);
+      if (err == cudaSuccess) count_launch();
+    }
+  }
+  if (d_partials != nullptr) cudaFreeAsync(d_partials, stream);
+  if (d_kf != nullptr) cudaFreeAsync(d_kf, stream);
+  return check_cuda(err, "rollout kernel launch");
+}
+
+}  // namespace
+
+extern "C" int bgr_rollout(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
+                           const float* d_params, const double* d_init_state, float* d_metrics, int32_t* d_status,
+                           double* d_traj, double* d_aggregate, void* stream) {
+  StepPlumbing sp;
+  return rollout_impl(track, cfg, n_episodes, d_params, d_init_state, d_metrics, d_status, d_traj, d_aggregate, sp,
+                      static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+
+// Stream-ordered scratch that is released when the scope ends.
+struct Scratch {
+  cudaStream_t stream;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, stream);
+  }
+  template <typename T>
+  int get(T** out, size_t count) {
+    *out = nullptr;
+    if (count == 0) count = 1;
+    void* p = nullptr;
+    int rc = check_cuda(cudaMallocAsync(&p, count * sizeof(T), stream), "cudaMallocAsync");
+    if (rc != BGR_OK) return rc;
+    ptrs.push_back(p);
+    *out = static_cast<T*>(p);
+    return BGR_OK;
+  }
+};
+
+struct DeviceScope {
+  int prev = 0;
+  explicit DeviceScope(int dev) {
+    cudaGetDevice(&prev);
+    cudaSetDevice(dev);
+  }
+  ~DeviceScope() { cudaSetDevice(prev); }
+};
+
+#define BGR_TRY(expr)            \
+  do {                           \
+    int rc_ = (expr);            \
+    if (rc_ != BGR_OK) return rc_; \
+  } while (0)
+
+}  // namespace
+
+extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
+                                const float* h_params, const double* h_init_state, float* h_metrics,
+                                int32_t* h_status, double* h_traj, double* h_aggregate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BGR_TRY(validate_cfg(track, cfg, "bgr_rollout_host"));
+  if (n_episodes < 0) {
+    set_error("bgr_rollout_host: n_episodes < 0");
+    return BGR_ERR_BAD_ARG;
+  }
+  if (n_episodes > 0 && (h_params == nullptr || h_init_state == nullptr || h_metrics == nullptr || h_status == nullptr)) {
+    set_error("bgr_rollout_host: h_params / h_init_state / h_metrics / h_status is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  DeviceScope dev(track->device);
+  Scratch sc(stream);
+  const size_t E = static_cast<size_t>(n_episodes);
+  float* d_params;
+  double* d_init;
+  float* d_metrics;
+  int32_t* d_status;
+  double* d_traj = nullptr;
+  double* d_agg = nullptr;
+  BGR_TRY(sc.get(&d_params, E * BGR_N_PARAMS));
+  BGR_TRY(sc.get(&d_init, E * BGR_N_STATE));
+  BGR_TRY(sc.get(&d_metrics, E * BGR_N_METRICS));
+  BGR_TRY(sc.get(&d_status, E * BGR_N_STATUS));
+  const size_t traj_count = E * static_cast<size_t>(cfg->max_steps) * BGR_N_TRAJ;
+  if (h_traj != nullptr) {
+    BGR_TRY(sc.get(&d_traj, traj_count));
+    BGR_CUDA(cudaMemsetAsync(d_traj, 0, traj_count * sizeof(double), stream));
+  }
+  if (h_aggregate != nullptr) BGR_TRY(sc.get(&d_agg, BGR_N_AGG));
+  if (E > 0) {
+    BGR_CUDA(cudaMemcpyAsync(d_params, h_params, E * BGR_N_PARAMS * sizeof(float), cudaMemcpyHostToDevice, stream));
+    BGR_CUDA(cudaMemcpyAsync(d_init, h_init_state, E * BGR_N_STATE * sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  StepPlumbing sp;
+  BGR_TRY(rollout_impl(track, cfg, n_episodes, d_params, d_init, d_metrics, d_status, d_traj, d_agg, sp, stream));
+  if (E > 0) {
+    BGR_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, E * BGR_N_METRICS * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    BGR_CUDA(cudaMemcpyAsync(h_status, d_status, E * BGR_N_STATUS * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    if (h_traj != nullptr)
+      BGR_CUDA(cudaMemcpyAsync(h_traj, d_traj, traj_count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  }
+  if (h_aggregate != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(h_aggregate, d_agg, BGR_N_AGG * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  BGR_CUDA(cudaStreamSynchronize(stream));
+  return BGR_OK;
+}
+
+extern "C" int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg_in, int32_t phases, int64_t n,
+                             const float* h_params, double* h_state, int32_t* h_target_ind, double* h_ctrl,
+                             const double* h_cmd, double* h_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BGR_TRY(validate_cfg(track, cfg_in, "bgr_step_host"));
+  if (n < 1 || h_params == nullptr || h_state == nullptr) {
+    set_error("bgr_step_host: need n >= 1, h_params and h_state");
+    return BGR_ERR_BAD_ARG;
+  }
+  const int32_t all = BGR_PHASE_STEER | BGR_PHASE_ACCEL | BGR_PHASE_MODEL | BGR_PHASE_ERRORS | BGR_PHASE_KAPPA_GIVEN;
+  if ((phases & ~all) != 0 || (phases & all) == 0) {
+    set_error("bgr_step_host: phases 0x%x is not a combination of BGR_PHASE_*", phases);
+    return BGR_ERR_BAD_ARG;
+  }
+  const bool need_cmd = !(phases & BGR_PHASE_STEER) || !(phases & BGR_PHASE_ACCEL) || (phases & BGR_PHASE_KAPPA_GIVEN);
+  if (need_cmd && h_cmd == nullptr) {
+    set_error("bgr_step_host: h_cmd is required when a law phase is off or the curvature is given");
+    return BGR_ERR_BAD_ARG;
+  }
+  bgr_rollout_cfg_t cfg = *cfg_in;
+  cfg.max_steps = 1;
+  cfg.laps_target = 0;
+  DeviceScope dev(track->device);
+  Scratch sc(stream);
+  const size_t E = static_cast<size_t>(n);
+  float* d_params;
+  double *d_state, *d_state_out, *d_ctrl_in, *d_ctrl_out, *d_cmd = nullptr, *d_out;
+  float* d_metrics;
+  int32_t *d_status, *d_ti_in, *d_ti_out;
+  BGR_TRY(sc.get(&d_params, E * BGR_N_PARAMS));
+  BGR_TRY(sc.get(&d_state, E * BGR_N_STATE));
+  BGR_TRY(sc.get(&d_state_out, E * BGR_N_STATE));
+  BGR_TRY(sc.get(&d_ctrl_in, E * BGR_N_CTRL));
+  BGR_TRY(sc.get(&d_ctrl_out, E * BGR_N_CTRL));
+  BGR_TRY(sc.get(&d_out, E * BGR_N_OUT));
+  BGR_TRY(sc.get(&d_metrics, E * BGR_N_METRICS));
+  BGR_TRY(sc.get(&d_status, E * BGR_N_STATUS));
+  BGR_TRY(sc.get(&d_ti_in, E));
+  BGR_TRY(sc.get(&d_ti_out, E));
+  BGR_CUDA(cudaMemcpyAsync(d_params, h_params, E * BGR_N_PARAMS * sizeof(float), cudaMemcpyHostToDevice, stream));
+  BGR_CUDA(cudaMemcpyAsync(d_state, h_state, E * BGR_N_STATE * sizeof(double), cudaMemcpyHostToDevice, stream));
+  if (h_ctrl != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(d_ctrl_in, h_ctrl, E * BGR_N_CTRL * sizeof(double), cudaMemcpyHostToDevice, stream));
+  else
+    BGR_CUDA(cudaMemsetAsync(d_ctrl_in, 0, E * BGR_N_CTRL * sizeof(double), stream));
+  if (h_target_ind != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(d_ti_in, h_target_ind, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  else
+    BGR_CUDA(cudaMemsetAsync(d_ti_in, 0, E * sizeof(int32_t), stream));
+  if (h_cmd != nullptr) {
+    BGR_TRY(sc.get(&d_cmd, E * BGR_N_CMD));
+    BGR_CUDA(cudaMemcpyAsync(d_cmd, h_cmd, E * BGR_N_CMD * sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  StepPlumbing sp;
+  sp.phases = phases;
+  sp.ctrl_in = d_ctrl_in;
+  sp.ctrl_out = d_ctrl_out;
+  sp.ti_in = d_ti_in;
+  sp.ti_out = d_ti_out;
+  sp.state_out = d_state_out;
+  sp.cmd = d_cmd;
+  sp.step_out = d_out;
+  sp.force_full = true;
+  BGR_TRY(rollout_impl(track, &cfg, n, d_params, d_state, d_metrics, d_status, nullptr, nullptr, sp, stream));
+  if (phases & BGR_PHASE_MODEL)
+    BGR_CUDA(cudaMemcpyAsync(h_state, d_state_out, E * BGR_N_STATE * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (h_ctrl != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(h_ctrl, d_ctrl_out, E * BGR_N_CTRL * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (h_target_ind != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(h_target_ind, d_ti_out, E * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  if (h_out != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(h_out, d_out, E * BGR_N_OUT * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  BGR_CUDA(cudaStreamSynchronize(stream));
+  return BGR_OK;
+}
+
+// ================================================================================================
+// MPC candidate evaluation
+// ================================================================================================
+static int validate_mpc(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes, int32_t K,
+                        const char* who) {
+  if (track == nullptr || cfg == nullptr) {
+    set_error("%s: track / cfg is NULL", who);
+    return BGR_ERR_BAD_ARG;
+  }
+  if (cfg->horizon < 1 || cfg->horizon > 64 || !(cfg->dt > 0.0) || !(cfg->wheelbase > 0.0) || cfg->precision < 0 ||
+      cfg->precision > 1) {
+    set_error("%s: need 1 <= horizon <= 64, dt > 0, wheelbase > 0 (got %d, %g, %g)", who, cfg->horizon, cfg->dt,
+              cfg->wheelbase);
+    return BGR_ERR_BAD_ARG;
+  }
+  for (int i = 0; i < 4; ++i) {
+    if (cfg->q[i] < 0.0 || (i < 2 && cfg->r[i] < 0.0)) {
+      set_error("%s: Q and R weights must be >= 0 (costs are compared through their bit patterns)", who);
+      return BGR_ERR_BAD_ARG;
+    }
+  }
+  if (n_episodes < 0 || K < 1) {
+    set_error("%s: need n_episodes >= 0 and n_candidates >= 1", who);
+    return BGR_ERR_BAD_ARG;
+  }
+  return BGR_OK;
+}
+
+extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                            const double* d_state, const int32_t* d_ref_start, const int32_t* d_ref_len,
+                            const float* d_bank, int32_t n_candidates, float* d_best_u, float* d_best_cost,
+                            int32_t* d_best_idx, float* d_costs, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BGR_TRY(validate_mpc(track, cfg, n_episodes, n_candidates, "bgr_mpc_eval"));
+  if (n_episodes == 0) return BGR_OK;
+  if (d_state == nullptr || d_ref_start == nullptr || d_bank == nullptr) {
+    set_error("bgr_mpc_eval: d_state / d_ref_start / d_bank is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(d_bank) & 7) {
+    set_error("bgr_mpc_eval: d_bank must be 8-byte aligned");
+    return BGR_ERR_BAD_ARG;
+  }
+  DeviceScope dev(track->device);
+  DeviceInfo di;
+  BGR_TRY(device_info(track->device, &di));
+  Scratch sc(stream);
+  unsigned long long* d_packed;
+  BGR_TRY(sc.get(&d_packed, static_cast<size_t>(n_episodes)));
+  BGR_CUDA(cudaMemsetAsync(d_packed, 0xff, static_cast<size_t>(n_episodes) * sizeof(unsigned long long), stream));
+  MpcArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.trk = track->view();
+  A.state = d_state;
+  A.ref_start = d_ref_start;
+  A.ref_len = d_ref_len;
+  A.bank = d_bank;
+  A.packed = d_packed;
+  A.costs = d_costs;
+  A.n_episodes = n_episodes;
+  A.K = n_candidates;
+  A.H = cfg->horizon;
+  A.dt = cfg->dt;
+  A.wheelbase = cfg->wheelbase;
+  A.target_speed = cfg->target_speed;
+  A.q0 = cfg->q[0];
+  A.q1 = cfg->q[1];
+  A.q2 = cfg->q[2];
+  A.q3 = cfg->q[3];
+  A.r0 = cfg->r[0];
+  A.r1 = cfg->r[1];
+  BGR_TRY(ensure_events(track->device));
+  BGR_CUDA(cudaEventRecord(g_last.start, stream));
+  BGR_CUDA(launch_mpc(A, cfg->precision, stream, di.sm_count));
+  count_launch();
+  BGR_CUDA(cudaEventRecord(g_last.stop, stream));
+  g_last.valid = true;
+  BGR_CUDA(launch_mpc_finalize(d_packed, d_bank, cfg->horizon, n_episodes, static_cast<float>(cfg->max_accel),
+                               static_cast<float>(cfg->max_decel), static_cast<float>(cfg->max_steer), d_best_u,
+                               d_best_cost, d_best_idx, stream));
+  count_launch();
+  return BGR_OK;
+}
+
+extern "C" int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                                 const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
+                                 const float* h_bank, int32_t n_candidates, float* h_best_u, float* h_best_cost,
+                                 int32_t* h_best_idx, float* h_costs, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BGR_TRY(validate_mpc(track, cfg, n_episodes, n_candidates, "bgr_mpc_eval_host"));
+  if (n_episodes == 0) return BGR_OK;
+  if (h_state == nullptr || h_ref_start == nullptr || h_bank == nullptr) {
+    set_error("bgr_mpc_eval_host: h_state / h_ref_start / h_bank is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  DeviceScope dev(track->device);
+  Scratch sc(stream);
+  const size_t E = static_cast<size_t>(n_episodes), K = static_cast<size_t>(n_candidates);
+  const size_t bank_count = K * static_cast<size_t>(cfg->horizon) * 2;
+  double* d_state;
+  int32_t *d_start, *d_len = nullptr, *d_idx;
+  float *d_bank, *d_u, *d_cost, *d_costs = nullptr;
+  BGR_TRY(sc.get(&d_state, E * 4));
+  BGR_TRY(sc.get(&d_start, E));
+  BGR_TRY(sc.get(&d_bank, bank_count));
+  BGR_TRY(sc.get(&d_u, E * 2));
+  BGR_TRY(sc.get(&d_cost, E));
+  BGR_TRY(sc.get(&d_idx, E));
+  BGR_CUDA(cudaMemcpyAsync(d_state, h_state, E * 4 * sizeof(double), cudaMemcpyHostToDevice, stream));
+  BGR_CUDA(cudaMemcpyAsync(d_start, h_ref_start, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  BGR_CUDA(cudaMemcpyAsync(d_bank, h_bank, bank_count * sizeof(float), cudaMemcpyHostToDevice, stream));
+  if (h_ref_len != nullptr) {
+    BGR_TRY(sc.get(&d_len, E));
+    BGR_CUDA(cudaMemcpyAsync(d_len, h_ref_len, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  }
+  if (h_costs != nullptr) BGR_TRY(sc.get(&d_costs, E * K));
+  BGR_TRY(bgr_mpc_eval(track, cfg, n_episodes, d_state, d_start, d_len, d_bank, n_candidates, d_u, d_cost, d_idx,
+                       d_costs, stream));
+  if (h_best_u != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(h_best_u, d_u, E * 2 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  if (h_best_cost != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(h_best_cost, d_cost, E * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  if (h_best_idx != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(h_best_idx, d_idx, E * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  if (h_costs != nullptr)
+    BGR_CUDA(cudaMemcpyAsync(h_costs, d_costs, E * K * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  BGR_CUDA(cudaStreamSynchronize(stream));
+  return BGR_OK;
+}
+
+// ================================================================================================
+// FP32 peak probe
+// ================================================================================================
+extern "C" int bgr_fp32_peak_probe(int device, double* out_tflops, double* out_ginst_per_s) {
+  int n_dev = 0;
+  BGR_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) {
+    set_error("bgr_fp32_peak_probe: device %d out of range", device);
+    return BGR_ERR_BAD_ARG;
+  }
+  DeviceScope dev(device);
+  DeviceInfo di;
+  BGR_TRY(device_info(device, &di));
+  const int grid = di.sm_count * 8;
+  const int iters = 1 << 14;
+  float* d_out = nullptr;
+  BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_out), static_cast<size_t>(grid) * 256 * sizeof(float)));
+  cudaEvent_t a, b;
+  BGR_CUDA(cudaEventCreate(&a));
+  BGR_CUDA(cudaEventCreate(&b));
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(a, nullptr);
+    cudaError_t err = launch_fp32_probe(d_out, grid, iters, nullptr);
+    cudaEventRecord(b, nullptr);
+    if (err != cudaSuccess || cudaEventSynchronize(b) != cudaSuccess) {
+      cudaFree(d_out);
+      return check_cuda(err != cudaSuccess ? err : cudaGetLastError(), "fp32 probe");
+    }
+    count_launch();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0) best_ms = std::min(best_ms, static_cast<double>(ms));
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d_out);
+  // 16 independent FMA chains per thread per iteration
+  const double fmas = static_cast<double>(grid) * 256.0 * iters * 16.0;
+  if (out_tflops != nullptr) *out_tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+  if (out_ginst_per_s != nullptr) *out_ginst_per_s = fmas / (best_ms * 1e-3) / 1e9;
+  return BGR_OK;
+}

@@ -1,0 +1,238 @@
+// Device-side helpers shared by the rollout / step / MPC kernels (sm_100a).
+//
+// Everything is templated on `Real`:
+//   float  -- production path: the tracking laws, tyre model and nearest/look-ahead searches run in
+//             fp32; the four integrators x, y, yaw, v are carried in fp64 and positions are handed to
+//             the fp32 code as (rounded, residual) pairs so that waypoint offsets lose nothing;
+//   double -- audit path: every operation in fp64, in the reference's operation order
+//             (compiled with --fmad=false so nothing is contracted).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/bgr_rollout.h"
+
+namespace bgr {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 2.0 * 3.14159265358979323846;
+constexpr int kRolloutThreads = 256;
+
+struct alignas(32) D4 {
+  double x, y, z, w;
+};
+
+template <typename Real>
+struct RT;
+template <>
+struct RT<float> {
+  using R2 = float2;
+  using R4 = float4;
+};
+template <>
+struct RT<double> {
+  using R2 = double2;
+  using R4 = D4;
+};
+
+// Device view of a track handle.  Per-waypoint tables (base lap, n_pad = n rounded up to 4):
+//   xy    : (x, y)                                 nodes/planner.py:88
+//   attr  : (kappa, path_yaw, sin path_yaw, cos path_yaw)   nodes/planner.py:89, core/controllers.py:361-368
+//   guard2: squared exactness-guard radius of the local nearest search
+struct TrackView {
+  const float2* xy_f;
+  const float4* attr_f;
+  const double2* xy_d;
+  const D4* attr_d;
+  const float* guard2;
+  const int32_t* cone_range;  // [n] (first << 10) | count  into cone_list
+  const int32_t* cone_list;
+  const double2* cones;       // [n_cones]
+  int32_t n;
+  int32_t n_pad;
+  int32_t closed;
+  int32_t n_cones;
+  float ds_max;
+};
+
+struct RolloutArgs {
+  TrackView trk;
+  const float* params;
+  const double* init;
+  float* metrics;
+  int32_t* status;
+  double* traj;
+  const double* kf_gain;  // [kf_len][2] shared Kalman gain sequence (LQG) or nullptr
+  int32_t kf_len;
+  double* block_partials; // [gridDim.x][BGR_N_AGG] or nullptr
+  long long n_episodes;
+  long long episode_id_base;
+  int32_t max_steps;
+  int32_t laps;
+  int32_t laps_target;
+  int32_t n_total;  // PP: n * laps; Stanley: n
+  double dt, wheelbase, l_f, l_r, max_steer, max_accel, max_decel;
+  double hit_radius, tie_eps;
+  double lqr_k0, lqr_k1;
+  double sigma_xy, sigma_yaw, sigma_v, sigma_cone;
+  uint32_t seed;
+  int32_t cones_on;
+  int32_t noise_on;
+  // single-step plumbing (EXTRAS kernels only; all nullptr for a rollout)
+  int32_t phases;
+  const double* ctrl_in;   // [E][BGR_N_CTRL]
+  double* ctrl_out;
+  const int32_t* ti_in;    // [E]
+  int32_t* ti_out;
+  double* state_out;       // [E][BGR_N_STATE] final state in fp64
+  const double* cmd;       // [E][BGR_N_CMD] (steer, accel, kappa) used for switched-off phases
+  double* step_out;        // [E][BGR_N_OUT] outputs of the LAST executed step
+};
+
+// ------------------------------------------------------------------------------------------------
+// TMA (bulk async copy) staging of the track tables into shared memory: one elected thread arms an
+// mbarrier with the byte count and issues cp.async.bulk per table (SASS: UBLKCP); everybody waits on
+// the barrier phase.  Sizes and addresses are multiples of 16 B by construction (n_pad % 4 == 0).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// normalize_angle (core/controllers.py:592-603): (angle + pi) % (2 pi) - pi with floor-mod => [-pi, pi)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double normalize_angle(double a) {
+  double t = a + kPi;
+  double m = fmod(t, kTwoPi);
+  if (m != 0.0) {
+    if (m < 0.0) m += kTwoPi;
+  } else {
+    m = 0.0;
+  }
+  return m - kPi;
+}
+
+// fp32 version for arguments known to lie in (-3 pi, 3 pi) -- every call site subtracts two angles
+// that are each within [-pi, pi] (+ one atan2).  Two-term 2 pi keeps the result accurate to an ulp.
+__device__ __forceinline__ float normalize_angle(float a) {
+  const float kPiF = 3.14159274101257324f;       // float(pi)
+  const float kTwoPiHi = 6.28318548202514648f;   // float(2 pi)
+  const float kTwoPiLo = -1.74845553146951715e-7f;  // 2 pi - float(2 pi)
+  if (a >= kPiF) {
+    a = (a - kTwoPiHi) - kTwoPiLo;
+  } else if (a < -kPiF) {
+    a = (a + kTwoPiHi) + kTwoPiLo;
+  }
+  return a;
+}
+
+// Heading handed to the laws.  double: the unwrapped yaw itself (reference semantics).  float: yaw
+// reduced to [-pi, pi] in fp64 first (yaw is never wrapped by the vehicle model, car_state.py:217, and
+// grows to tens of radians; fp32 would lose 1e-6 rad there).
+template <typename Real>
+__device__ __forceinline__ Real heading_for_laws(double yaw);
+template <>
+__device__ __forceinline__ double heading_for_laws<double>(double yaw) {
+  return yaw;
+}
+template <>
+__device__ __forceinline__ float heading_for_laws<float>(double yaw) {
+  double k = rint(yaw * (1.0 / kTwoPi));
+  return static_cast<float>(fma(-k, kTwoPi, yaw));
+}
+
+template <typename Real>
+__device__ __forceinline__ Real clampr(Real v, Real lo, Real hi) {
+  return fmin(fmax(v, lo), hi);  // np.clip = minimum(maximum(v, lo), hi)
+}
+
+__device__ __forceinline__ void sincos_r(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void sincos_r(double a, double* s, double* c) {
+  *s = sin(a);
+  *c = cos(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11); identical integer stream to oracle/philox.py
+// ------------------------------------------------------------------------------------------------
+struct U4 {
+  uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                            uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return U4{c0, c1, c2, c3};
+}
+
+template <typename Real>
+__device__ __forceinline__ Real u01_24(uint32_t r) {
+  return (static_cast<Real>(r >> 8) + Real(0.5)) * Real(1.0 / 16777216.0);
+}
+
+// two Box-Muller pairs -> four standard normals (oracle/philox.py:gaussians4)
+template <typename Real>
+__device__ __forceinline__ void gaussians4(U4 r, Real z[4]) {
+  Real ua = u01_24<Real>(r.x), ub = u01_24<Real>(r.y), uc = u01_24<Real>(r.z), ud = u01_24<Real>(r.w);
+  Real ra = sqrt(Real(-2.0) * log(ua));
+  Real rc = sqrt(Real(-2.0) * log(uc));
+  Real s, c;
+  sincos_r(Real(kTwoPi) * ub, &s, &c);
+  z[0] = ra * c;
+  z[1] = ra * s;
+  sincos_r(Real(kTwoPi) * ud, &s, &c);
+  z[2] = rc * c;
+  z[3] = rc * s;
+}
+
+constexpr uint32_t kStreamObs = 0;
+constexpr uint32_t kStreamCone = 1;
+
+}  // namespace bgr

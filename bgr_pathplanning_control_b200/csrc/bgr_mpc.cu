@@ -1,0 +1,214 @@
+// MPC candidate-sequence rollout + cost evaluation (config 4).
+//
+// Replaces the cvxpy/OSQP solve inside MPCController.compute_control (core/controllers.py:486-568) by
+// scoring K candidate control sequences per episode with the reference's own cost (:545, :548) under
+// its own linearised dynamics (:522-527) and feasibility rule (:536), and taking the cheapest one.
+//
+// Mapping: ONE CANDIDATE PER THREAD.  A thread loads its candidate's H x (accel, steer) controls ONCE
+// into registers and then walks over a strided list of episodes, so the candidate bank is read from
+// HBM/L2 exactly once per CTA row and the inner loop touches only registers plus one broadcast
+// shared-memory word per stage (the per-episode, candidate-independent x/y cost: :523-524 make x and y
+// independent of the controls).  Candidate blocks of one episode meet through a 64-bit atomicMin on
+// (cost bits << 32 | candidate index): order independent, hence deterministic, and the lowest index
+// wins exact ties like np.argmin.  No tensor cores: there is no contraction here.
+#include "bgr_launch.cuh"
+
+namespace bgr {
+
+
+template <typename Real>
+struct EpisodeStage {
+  Real xy[kMpcMaxH + 1];  // Q0 ex^2 + Q1 ey^2 at stage k (k = H: terminal, :548)
+  Real yaw0, v0, c_yaw;   // c_yaw = v0 / WB (fp64 path) or v0 / WB * dt (fp32 path)
+  unsigned long long best;
+};
+
+// Stage the candidate-independent part of one episode (threads 0..H of the CTA).
+template <typename Real>
+__device__ __forceinline__ void stage_episode(const MpcArgs& A, long long e, EpisodeStage<Real>* st) {
+  const int t = threadIdx.x;
+  if (t > A.H) return;
+  const double* s = A.state + e * 4;
+  const double x0 = s[0], y0 = s[1], yaw0 = s[2], v0 = s[3];
+  const double cos_t = cos(yaw0), sin_t = sin(yaw0);               // :514-515
+  // x_t, y_t by the same repeated additions as :523-524
+  double sx = x0, sy = y0;
+  for (int k = 0; k < t; ++k) {
+    sx = sx + v0 * cos_t * A.dt;
+    sy = sy + v0 * sin_t * A.dt;
+  }
+  // reference point of stage t (:539-542); the terminal cost reuses the last stage's (:548)
+  const int n = A.trk.n;
+  const int start = A.ref_start[e];
+  int len = A.ref_len != nullptr ? A.ref_len[e] : (A.trk.closed ? 0x3fffffff : n - start);
+  if (len < 1) len = 1;
+  int k_ref = t < A.H ? t : A.H - 1;
+  if (k_ref >= len) k_ref = len - 1;
+  long long idx = static_cast<long long>(start) + k_ref;
+  if (A.trk.closed) idx %= n;
+  else if (idx > n - 1) idx = n - 1;
+  const double2 p = A.trk.xy_d[idx];
+  const double ex = sx - p.x, ey = sy - p.y;
+  st->xy[t] = static_cast<Real>(A.q0 * ex * ex + A.q1 * ey * ey);
+  if (t == 0) {
+    st->yaw0 = static_cast<Real>(yaw0);
+    st->v0 = static_cast<Real>(v0);
+    if constexpr (sizeof(Real) == 8) st->c_yaw = static_cast<Real>(v0 / A.wheelbase);
+    else st->c_yaw = static_cast<Real>(v0 / A.wheelbase * A.dt);
+    st->best = ~0ull;
+  }
+}
+
+template <typename Real, int HT>  // HT > 0: horizon known at compile time, controls in registers
+__global__ void __launch_bounds__(kMpcThreads) mpc_kernel(const __grid_constant__ MpcArgs A) {
+  __shared__ EpisodeStage<Real> stage[2];
+  const int H = HT > 0 ? HT : A.H;
+  const int c = blockIdx.x * kMpcThreads + threadIdx.x;
+  const bool cvalid = c < A.K;
+  const int lane = threadIdx.x & 31;
+
+  constexpr int HR = HT > 0 ? HT : 1;
+  Real ua[HR], us[HR];
+  const float2* my = reinterpret_cast<const float2*>(A.bank) + static_cast<size_t>(cvalid ? c : 0) * H;
+  if constexpr (HT > 0) {
+#pragma unroll
+    for (int k = 0; k < HT; ++k) {
+      const float2 u = __ldg(my + k);
+      ua[k] = u.x;
+      us[k] = u.y;
+    }
+  }
+
+  const Real dt = static_cast<Real>(A.dt);
+  const Real vt = static_cast<Real>(A.target_speed);
+  const Real q2 = static_cast<Real>(A.q2), q3 = static_cast<Real>(A.q3);
+  const Real r0 = static_cast<Real>(A.r0), r1 = static_cast<Real>(A.r1);
+
+  long long e = blockIdx.y;
+  int b = 0;
+  if (e < A.n_episodes) stage_episode<Real>(A, e, &stage[0]);
+  __syncthreads();
+  for (; e < A.n_episodes; e += gridDim.y, b ^= 1) {
+    const long long e_next = e + gridDim.y;
+    if (e_next < A.n_episodes) stage_episode<Real>(A, e_next, &stage[b ^ 1]);
+
+    const EpisodeStage<Real>& S = stage[b];
+    Real yaw = S.yaw0, v = S.v0, cost = 0, vmin = Real(0);
+    const Real cy = S.c_yaw;
+    auto stage_step = [&](Real a, Real s, int k) {
+      const Real ev = v - vt;
+      // :545  quad_form(x - ref, Q) then quad_form(u, R)
+      if constexpr (sizeof(Real) == 8) {
+        cost += S.xy[k] + q2 * yaw * yaw + q3 * ev * ev;
+        cost += r0 * a * a + r1 * s * s;
+        yaw = yaw + cy * s * dt;                                  // :525
+        v = v + a * dt;                                           // :526
+      } else {
+        cost += fmaf(q3 * ev, ev, fmaf(q2 * yaw, yaw, S.xy[k]));
+        cost += fmaf(r0 * a, a, r1 * s * s);
+        yaw = fmaf(cy, s, yaw);
+        v = fmaf(a, dt, v);
+      }
+      vmin = fmin(vmin, v);                                       // :536  v_{k+1} >= 0
+    };
+    if constexpr (HT > 0) {
+#pragma unroll
+      for (int k = 0; k < HT; ++k) stage_step(ua[k], us[k], k);
+    } else {
+      for (int k = 0; k < H; ++k) {
+        const float2 u = __ldg(my + k);
+        stage_step(static_cast<Real>(u.x), static_cast<Real>(u.y), k);
+      }
+    }
+    {
+      const Real ev = v - vt;                                      // :548 terminal, last stage's reference
+      if constexpr (sizeof(Real) == 8) cost += S.xy[H] + q2 * yaw * yaw + q3 * ev * ev;
+      else cost += fmaf(q3 * ev, ev, fmaf(q2 * yaw, yaw, S.xy[H]));
+    }
+    float costf = static_cast<float>(cost);
+    if (!(vmin >= Real(0)) || !cvalid || !(costf == costf)) costf = INFINITY;   // infeasible / NaN
+    if (A.costs != nullptr && cvalid) A.costs[static_cast<size_t>(e) * A.K + c] = costf;
+
+    // warp argmin with np.argmin's first-minimum rule: min over cost bits (costs are >= 0, so the
+    // IEEE bit pattern is order preserving), then the lowest lane holding it
+    const uint32_t bits = __float_as_uint(costf);
+    const uint32_t wmin = __reduce_min_sync(0xffffffffu, bits);
+    const uint32_t who = __ballot_sync(0xffffffffu, bits == wmin);
+    if (lane == __ffs(who) - 1 && wmin < 0x7f800000u) {
+      atomicMin(&stage[b].best, (static_cast<unsigned long long>(wmin) << 32) | static_cast<uint32_t>(c));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && stage[b].best != ~0ull) atomicMin(A.packed + e, stage[b].best);
+    // stage[b] is rewritten only after the NEXT iteration's barrier, so thread 0's read above is safe
+  }
+}
+
+// packed (cost bits, index) -> (acceleration, steering) with the return convention of :565-568
+__global__ void mpc_finalize_kernel(const unsigned long long* __restrict__ packed, const float* __restrict__ bank,
+                                    int H, long long n_episodes, float max_accel, float max_decel, float max_steer,
+                                    float* __restrict__ best_u, float* __restrict__ best_cost,
+                                    int32_t* __restrict__ best_idx) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_episodes) return;
+  const unsigned long long p = packed[e];
+  if (p == ~0ull) {  // no feasible candidate: the solver-failure fallback (:558-562)
+    if (best_u != nullptr) {
+      best_u[2 * e] = 0.0f;
+      best_u[2 * e + 1] = -0.0f;
+    }
+    if (best_cost != nullptr) best_cost[e] = INFINITY;
+    if (best_idx != nullptr) best_idx[e] = -1;
+    return;
+  }
+  const int idx = static_cast<int>(p & 0xffffffffull);
+  const float2 u0 = reinterpret_cast<const float2*>(bank)[static_cast<size_t>(idx) * H];
+  if (best_u != nullptr) {
+    best_u[2 * e] = fminf(fmaxf(u0.x, max_decel), max_accel);             // :565
+    best_u[2 * e + 1] = -fminf(fmaxf(u0.y, -max_steer), max_steer);       // :566, :568
+  }
+  if (best_cost != nullptr) best_cost[e] = __uint_as_float(static_cast<uint32_t>(p >> 32));
+  if (best_idx != nullptr) best_idx[e] = idx;
+}
+
+template <typename Real, int HT>
+static cudaError_t launch_mpc_t(const MpcArgs& A, cudaStream_t stream, int sm_count) {
+  auto kern = mpc_kernel<Real, HT>;
+  int per_sm = 1;
+  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMpcThreads, 0);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) per_sm = 1;
+  const int gx = (A.K + kMpcThreads - 1) / kMpcThreads;
+  long long gy = (static_cast<long long>(sm_count) * per_sm) / gx;
+  if (gy < 1) gy = 1;
+  if (gy > A.n_episodes) gy = A.n_episodes;
+  if (gy > 65535) gy = 65535;
+  kern<<<dim3(gx, static_cast<unsigned>(gy)), kMpcThreads, 0, stream>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mpc(const MpcArgs& A, int precision, cudaStream_t stream, int sm_count) {
+  if (precision == BGR_PRECISION_FP64) {
+    switch (A.H) {
+      case 10: return launch_mpc_t<double, 10>(A, stream, sm_count);
+      default: return launch_mpc_t<double, 0>(A, stream, sm_count);
+    }
+  }
+  switch (A.H) {
+    case 10: return launch_mpc_t<float, 10>(A, stream, sm_count);
+    case 20: return launch_mpc_t<float, 20>(A, stream, sm_count);
+    case 30: return launch_mpc_t<float, 30>(A, stream, sm_count);
+    default: return launch_mpc_t<float, 0>(A, stream, sm_count);
+  }
+}
+
+cudaError_t launch_mpc_finalize(const unsigned long long* packed, const float* bank, int H, long long n_episodes,
+                                float max_accel, float max_decel, float max_steer, float* best_u,
+                                float* best_cost, int32_t* best_idx, cudaStream_t stream) {
+  const int threads = 256;
+  const long long blocks = (n_episodes + threads - 1) / threads;
+  mpc_finalize_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      packed, bank, H, n_episodes, max_accel, max_decel, max_steer, best_u, best_cost, best_idx);
+  return cudaGetLastError();
+}
+
+}  // namespace bgr

@@ -1,0 +1,39 @@
+// Host-side track handle: derived per-waypoint tables + device residency.
+#pragma once
+
+#include <vector>
+
+#include "bgr_device.cuh"
+
+struct bgr_track {
+  int device = 0;
+  int n = 0, n_pad = 0, closed = 0, n_cones = 0;
+  double cone_reach = 0.0;
+  // device tables
+  float2* xy_f = nullptr;
+  float4* attr_f = nullptr;
+  double2* xy_d = nullptr;
+  bgr::D4* attr_d = nullptr;
+  float* guard2 = nullptr;
+  int32_t* cone_range = nullptr;
+  int32_t* cone_list = nullptr;
+  double2* cones = nullptr;
+  // host copies
+  std::vector<double> x, y, kappa, path_yaw, guard_radius;
+  double ds_min = 0, ds_max = 0, guard_min = 0, guard_median = 0;
+
+  bgr::TrackView view() const {
+    bgr::TrackView v;
+    v.xy_f = xy_f; v.attr_f = attr_f; v.xy_d = xy_d; v.attr_d = attr_d; v.guard2 = guard2;
+    v.cone_range = cone_range; v.cone_list = cone_list; v.cones = cones;
+    v.n = n; v.n_pad = n_pad; v.closed = closed; v.n_cones = n_cones;
+    v.ds_max = static_cast<float>(ds_max);
+    return v;
+  }
+};
+
+namespace bgr {
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t err, const char* what);
+void count_launch(int n = 1);
+}  // namespace bgr

@@ -1,0 +1,402 @@
+"""Batched entry points: (episodes x params) tensors in, per-episode lap metrics out.
+
+This is the "batched entry point taking (episodes x params) tensors" of the north star.  Everything
+numeric happens in the sm_100a kernels behind the C ABI (``_abi.py`` -> ``libbgr_rollout.so``); torch is
+used for device memory and streams only.  No CPU fallback: without the library or without a CUDA device
+these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi as abi
+from .vehicle_config import conf
+
+_STEER = {"pure_pursuit": abi.STEER_PURE_PURSUIT, "stanley": abi.STEER_STANLEY}
+_ACCEL = {"pid": abi.ACCEL_PID, "lqg": abi.ACCEL_LQG}
+_MODEL = {"kinematic": abi.MODEL_KINEMATIC, "dynamic": abi.MODEL_DYNAMIC}
+_PRECISION = {"fp32": abi.PRECISION_FP32, "fp64": abi.PRECISION_FP64}
+
+
+def _ptr(a):
+    """Raw address of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def _np(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return a
+
+
+class Track:
+    """Device-resident centreline handle (``bgr_track_t``): what the reference hands its controllers every
+    call as ``path`` (N,3) + ``curve`` (nodes/controller.py:56,62), uploaded once."""
+
+    def __init__(self, x, y, kappa=None, closed=True, cones=None, cone_reach=None, device=0):
+        lib = abi.load()
+        self.x = _np(x, np.float64)
+        self.y = _np(y, np.float64, self.x.shape)
+        self.kappa = np.zeros_like(self.x) if kappa is None else _np(kappa, np.float64, self.x.shape)
+        self.cones = np.zeros((0, 2)) if cones is None else _np(cones, np.float64).reshape(-1, 2)
+        self.closed = bool(closed)
+        self.device = int(device)
+        self.cone_reach = float(cone_reach) if cone_reach is not None else 4.0
+        desc = abi.TrackDesc()
+        dp = C.POINTER(C.c_double)
+        desc.h_x = self.x.ctypes.data_as(dp)
+        desc.h_y = self.y.ctypes.data_as(dp)
+        desc.h_kappa = self.kappa.ctypes.data_as(dp)
+        desc.n = len(self.x)
+        desc.closed = int(self.closed)
+        desc.h_cones_xy = self.cones.ctypes.data_as(dp) if len(self.cones) else None
+        desc.n_cones = len(self.cones)
+        desc.cone_reach = self.cone_reach
+        self._h = C.c_void_p()
+        self._lib = lib
+        abi.check(lib.bgr_track_create(C.byref(desc), self.device, C.byref(self._h)))
+
+    @classmethod
+    def from_arrays(cls, t, device=0, cone_reach=None):
+        """From a ``tracks.TrackArrays``."""
+        return cls(t.x, t.y, t.kappa, t.closed, t.cones, cone_reach, device)
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("track handle is closed")
+        return self._h
+
+    @property
+    def n(self):
+        return len(self.x)
+
+    def info(self):
+        out = abi.TrackInfo()
+        abi.check(self._lib.bgr_track_info(self.handle, C.byref(out)))
+        return {k: getattr(out, k) for k, _ in abi.TrackInfo._fields_}
+
+    def tables(self):
+        """(path_yaw, guard_radius): per-waypoint heading (core/controllers.py:361-368) and the exactness
+        guard radius of the local nearest search."""
+        yaw = np.empty(self.n)
+        guard = np.empty(self.n)
+        abi.check(self._lib.bgr_track_tables(self.handle, yaw.ctypes.data, guard.ctypes.data))
+        return yaw, guard
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bgr_track_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class RolloutConfig:
+    """Mirror of ``bgr_rollout_cfg_t``; defaults are the reference's ``Vehicle_config`` values."""
+    steer: str = "pure_pursuit"      # PurePursuitController | StanleyController (live def)
+    accel: str = "pid"               # AccelerationPIDController | LQGAccelerationController
+    model: str = "kinematic"         # oracle-defined kinematic | DynamicBicycleModel
+    precision: str = "fp32"          # "fp64" = audit build, reference operation order
+    max_steps: int = 2000
+    laps: int = 1                    # PP: base lap tiled this many times (monotone target index)
+    laps_target: int = 0
+    audit: bool = False              # fill the near-tie audit channel (full kernel build)
+    dt: float = conf.dt
+    wheelbase: float = conf.WB
+    l_f: float = conf.l_f
+    l_r: float = conf.l_r
+    max_steer: float = conf.MAX_STEER
+    max_accel: float = conf.MAX_ACCEL
+    max_decel: float = conf.MAX_DECEL
+    hit_radius: float = 0.0
+    tie_eps: float = 0.0
+    sigma_xy: float = 0.0
+    sigma_yaw: float = 0.0
+    sigma_v: float = 0.0
+    sigma_cone: float = 0.0
+    noise_seed: int = 0
+    episode_id_base: int = 0
+
+    def to_struct(self):
+        c = abi.RolloutCfg()
+        try:
+            c.steer_kind, c.accel_kind = _STEER[self.steer], _ACCEL[self.accel]
+            c.model_kind, c.precision = _MODEL[self.model], _PRECISION[self.precision]
+        except KeyError as e:
+            raise ValueError(f"Unknown controller / model / precision: {e.args[0]}") from None
+        c.max_steps, c.laps, c.laps_target = int(self.max_steps), int(self.laps), int(self.laps_target)
+        c.flags = abi.CFG_AUDIT if self.audit else 0
+        for k in ("dt", "wheelbase", "l_f", "l_r", "max_steer", "max_accel", "max_decel", "hit_radius", "tie_eps",
+                  "sigma_xy", "sigma_yaw", "sigma_v", "sigma_cone"):
+            setattr(c, k, float(getattr(self, k)))
+        c.noise_seed = int(self.noise_seed) & 0xFFFFFFFF
+        c.episode_id_base = int(self.episode_id_base)
+        return c
+
+
+def default_params(n_episodes=1, dtype=np.float32):
+    """(E, 16) parameter rows filled with the reference defaults (vehicle_config.py:4-39; Stanley gains
+    from the factory, core/controllers.py:585)."""
+    p = np.zeros((n_episodes, abi.N_PARAMS), dtype=dtype)
+    p[:, abi.P_LF] = conf.LOOKAHEAD_DISTANCE
+    p[:, abi.P_KP], p[:, abi.P_KI], p[:, abi.P_KD] = conf.kp_accel, conf.ki_accel, conf.kd_accel
+    p[:, abi.P_TARGET_SPEED] = conf.TARGET_SPEED
+    p[:, abi.P_K_EXPO] = conf.k_expo
+    p[:, abi.P_K_STANLEY], p[:, abi.P_K_SOFT] = 1.0, 0.1
+    p[:, abi.P_MU], p[:, abi.P_C_F], p[:, abi.P_C_R] = conf.mu, conf.c_f, conf.c_r
+    p[:, abi.P_MASS], p[:, abi.P_I_Z] = conf.m, conf.I_z
+    return p
+
+
+def initial_states(track, n_episodes=1, index=0, lateral_offset=None, yaw_offset=None, v0=0.0):
+    """(E, 6) float64 initial rows ``[x, y, yaw, v, r, beta]`` on waypoint ``index`` of a
+    ``tracks.TrackArrays`` / ``Track``, heading along the tangent, optionally shifted sideways."""
+    n = len(track.x)
+    j = (index + 1) % n
+    yaw = float(np.arctan2(track.y[j] - track.y[index], track.x[j] - track.x[index]))
+    s = np.zeros((n_episodes, abi.N_STATE))
+    off = np.zeros(n_episodes) if lateral_offset is None else np.asarray(lateral_offset, dtype=np.float64)
+    s[:, abi.X] = track.x[index] - np.sin(yaw) * off
+    s[:, abi.Y] = track.y[index] + np.cos(yaw) * off
+    s[:, abi.YAW] = yaw + (0.0 if yaw_offset is None else np.asarray(yaw_offset, dtype=np.float64))
+    s[:, abi.V] = v0
+    return s
+
+
+@dataclass
+class RolloutResult:
+    """Per-episode outputs.  ``metrics`` (E, 12) float32 and ``status`` (E, 10) int32 follow the
+    ``BGR_M_*`` / ``BGR_S_*`` columns of the header; tensors live where the inputs lived."""
+    metrics: object
+    status: object
+    traj: object = None
+    aggregate: object = None
+    kernel_ms: float | None = None
+
+    def _col(self, a, i):
+        return a[:, i]
+
+    # the five scalars of preformance_analysis/metrics_calculator.py:1-8, per episode
+    @property
+    def lateral_error(self):
+        return self._col(self.metrics, abi.M_LAT_MEAN), self._col(self.metrics, abi.M_LAT_STD)
+
+    @property
+    def heading_error(self):
+        return self._col(self.metrics, abi.M_HEAD_MEAN), self._col(self.metrics, abi.M_HEAD_STD)
+
+    @property
+    def lap_time(self):
+        return self._col(self.metrics, abi.M_LAP_TIME)
+
+    @property
+    def cone_hits(self):
+        return self._col(self.status, abi.S_CONE_HITS)
+
+    @property
+    def steps(self):
+        return self._col(self.status, abi.S_STEPS)
+
+    @property
+    def flags(self):
+        return self._col(self.status, abi.S_FLAGS)
+
+    def final_state(self):
+        return self.metrics[:, abi.M_X:abi.M_BETA + 1]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def rollout(track, config, params, init_state, *, traj=False, aggregate=False, out=None, time_kernel=False):
+    """Run ``E`` closed-loop episodes on the track's GPU.
+
+    ``params`` (E, 16) float32 and ``init_state`` (E, 6) float64 are CUDA torch tensors on the track's
+    device (the zero-copy path) -- or numpy arrays, in which case the host-buffer entry point
+    ``bgr_rollout_host`` does the H2D/D2H copies and numpy arrays come back.
+    Asynchronous on the current torch stream for CUDA tensors.
+    """
+    lib = abi.load()
+    cfg = config.to_struct() if isinstance(config, RolloutConfig) else config
+    if isinstance(params, np.ndarray) or isinstance(init_state, np.ndarray):
+        return _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate)
+    torch = _torch()
+    E = int(params.shape[0])
+    if not (params.is_cuda and init_state.is_cuda):
+        raise ValueError("params and init_state must be CUDA tensors (or numpy arrays for the host entry point); "
+                         "there is no CPU path")
+    if params.device.index != track.device or init_state.device.index != track.device:
+        raise ValueError(f"inputs must live on the track's device cuda:{track.device}")
+    if params.dtype != torch.float32 or tuple(params.shape) != (E, abi.N_PARAMS) or not params.is_contiguous():
+        raise ValueError(f"params must be a contiguous float32 tensor of shape (E, {abi.N_PARAMS})")
+    if (init_state.dtype != torch.float64 or tuple(init_state.shape) != (E, abi.N_STATE)
+            or not init_state.is_contiguous()):
+        raise ValueError(f"init_state must be a contiguous float64 tensor of shape (E, {abi.N_STATE})")
+    dev = params.device
+    if out is not None:
+        metrics, status = out.metrics, out.status
+    else:
+        metrics = torch.empty((E, abi.N_METRICS), dtype=torch.float32, device=dev)
+        status = torch.empty((E, abi.N_STATUS), dtype=torch.int32, device=dev)
+    tr = None
+    if traj:
+        tr = torch.zeros((E, cfg.max_steps, abi.N_TRAJ), dtype=torch.float64, device=dev)
+    agg = None
+    if aggregate:
+        agg = out.aggregate if (out is not None and out.aggregate is not None) else torch.empty(
+            abi.N_AGG, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    abi.check(lib.bgr_rollout(track.handle, C.byref(cfg), E, _ptr(params), _ptr(init_state), _ptr(metrics),
+                              _ptr(status), _ptr(tr), _ptr(agg), stream))
+    ms = None
+    if time_kernel and E > 0:
+        v = C.c_double()
+        abi.check(lib.bgr_last_kernel_ms(C.byref(v)))
+        ms = v.value
+    return RolloutResult(metrics, status, tr, agg, ms)
+
+
+def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate):
+    params = _np(params, np.float32)
+    E = params.shape[0]
+    params = _np(params, np.float32, (E, abi.N_PARAMS))
+    init_state = _np(init_state, np.float64, (E, abi.N_STATE))
+    metrics = np.empty((E, abi.N_METRICS), dtype=np.float32)
+    status = np.empty((E, abi.N_STATUS), dtype=np.int32)
+    tr = np.zeros((E, cfg.max_steps, abi.N_TRAJ)) if traj else None
+    agg = np.empty(abi.N_AGG) if aggregate else None
+    abi.check(lib.bgr_rollout_host(track.handle, C.byref(cfg), E, _ptr(params), _ptr(init_state), _ptr(metrics),
+                                   _ptr(status), _ptr(tr), _ptr(agg), None))
+    return RolloutResult(metrics, status, tr, agg, None)
+
+
+def last_kernel_ms():
+    v = C.c_double()
+    abi.check(abi.load().bgr_last_kernel_ms(C.byref(v)))
+    return v.value
+
+
+def launch_count():
+    return int(abi.load().bgr_launch_count())
+
+
+def lqg_design(dt=conf.dt, n_steps=0):
+    """(K (2,), kalman_gains (n_steps, 2)): the LQR gain of ``control.dlqr`` (core/controllers.py:97) and
+    the data-independent Kalman gain sequence (:145-160) every episode shares."""
+    K = np.empty(2)
+    g = np.empty((n_steps, 2)) if n_steps > 0 else None
+    abi.check(abi.load().bgr_lqg_design(float(dt), int(n_steps), _ptr(K), _ptr(g)))
+    return K, g
+
+
+def fp32_peak_probe(device=0):
+    """(TFLOP/s, G lane-FMA/s) of an FFMA-chain microbenchmark: the roofline denominator."""
+    t, g = C.c_double(), C.c_double()
+    abi.check(abi.load().bgr_fp32_peak_probe(int(device), C.byref(t), C.byref(g)))
+    return t.value, g.value
+
+
+@dataclass
+class MpcConfig:
+    """Mirror of ``bgr_mpc_cfg_t``; defaults = MPCController as the factory builds it
+    (core/controllers.py:483-484, :587)."""
+    horizon: int = 10
+    dt: float = 0.05
+    precision: str = "fp32"
+    wheelbase: float = conf.WB
+    target_speed: float = conf.TARGET_SPEED
+    q: tuple = (1.0, 1.0, 0.5, 0.1)
+    r: tuple = (0.1, 0.1)
+    max_accel: float = conf.MAX_ACCEL
+    max_decel: float = conf.MAX_DECEL
+    max_steer: float = conf.MAX_STEER
+
+    def to_struct(self):
+        c = abi.MpcCfg()
+        c.horizon, c.precision = int(self.horizon), _PRECISION[self.precision]
+        c.dt, c.wheelbase, c.target_speed = float(self.dt), float(self.wheelbase), float(self.target_speed)
+        for i in range(4):
+            c.q[i] = float(self.q[i])
+        for i in range(2):
+            c.r[i] = float(self.r[i])
+        c.max_accel, c.max_decel, c.max_steer = float(self.max_accel), float(self.max_decel), float(self.max_steer)
+        return c
+
+
+@dataclass
+class MpcResult:
+    best_u: object        # (E, 2) float32 = (acceleration, steering) as compute_control returns them (:568)
+    best_cost: object     # (E,) float32, +inf when no candidate is feasible
+    best_idx: object      # (E,) int32, -1 when none is feasible
+    costs: object = None  # (E, K) float32 (+inf = infeasible), only on request
+    kernel_ms: float | None = None
+
+
+def candidate_bank(n_candidates=4096, horizon=30, seed=20261021, max_accel=conf.MAX_ACCEL, max_steer=conf.MAX_STEER):
+    """(K, H, 2) float32 = (accel, steer): uniform draws smoothed by a 3-tap moving average, candidate 0
+    all zeros.  Host numpy; the same bank feeds the oracle."""
+    rng = np.random.default_rng(seed)
+    u = np.empty((n_candidates, horizon, 2))
+    u[..., 0] = rng.uniform(-max_accel, max_accel, (n_candidates, horizon))
+    u[..., 1] = rng.uniform(-max_steer, max_steer, (n_candidates, horizon))
+    pad = np.concatenate([u[:, :1], u, u[:, -1:]], axis=1)
+    u = (pad[:, :-2] + pad[:, 1:-1] + pad[:, 2:]) / 3.0
+    u[0] = 0.0
+    return np.ascontiguousarray(u, dtype=np.float32)
+
+
+def mpc_evaluate(track, config, state, ref_start, bank, ref_len=None, *, return_costs=False, time_kernel=False):
+    """Score every candidate control sequence of ``bank`` (K, H, 2) for every episode state (E, 4) =
+    ``[x, y, yaw, v]`` and pick the cheapest feasible one.  CUDA tensors (zero copy, async) or numpy arrays
+    (host entry point)."""
+    lib = abi.load()
+    cfg = config.to_struct() if isinstance(config, MpcConfig) else config
+    if isinstance(state, np.ndarray):
+        state = _np(state, np.float64)
+        E = state.shape[0]
+        state = _np(state, np.float64, (E, 4))
+        ref_start = _np(ref_start, np.int32, (E,))
+        ref_len = None if ref_len is None else _np(ref_len, np.int32, (E,))
+        bank = _np(bank, np.float32)
+        K = bank.shape[0]
+        bank = _np(bank, np.float32, (K, cfg.horizon, 2))
+        u = np.empty((E, 2), np.float32)
+        cost = np.empty(E, np.float32)
+        idx = np.empty(E, np.int32)
+        costs = np.empty((E, K), np.float32) if return_costs else None
+        abi.check(lib.bgr_mpc_eval_host(track.handle, C.byref(cfg), E, _ptr(state), _ptr(ref_start), _ptr(ref_len),
+                                        _ptr(bank), K, _ptr(u), _ptr(cost), _ptr(idx), _ptr(costs), None))
+        return MpcResult(u, cost, idx, costs)
+    torch = _torch()
+    E, K = int(state.shape[0]), int(bank.shape[0])
+    for name, t, dt, shape in (("state", state, torch.float64, (E, 4)), ("ref_start", ref_start, torch.int32, (E,)),
+                               ("bank", bank, torch.float32, (K, cfg.horizon, 2))):
+        if not t.is_cuda or t.device.index != track.device or t.dtype != dt or tuple(t.shape) != shape \
+                or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous {dt} CUDA tensor of shape {shape} on cuda:{track.device}")
+    dev = state.device
+    u = torch.empty((E, 2), dtype=torch.float32, device=dev)
+    cost = torch.empty(E, dtype=torch.float32, device=dev)
+    idx = torch.empty(E, dtype=torch.int32, device=dev)
+    costs = torch.empty((E, K), dtype=torch.float32, device=dev) if return_costs else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    abi.check(lib.bgr_mpc_eval(track.handle, C.byref(cfg), E, _ptr(state), _ptr(ref_start), _ptr(ref_len), _ptr(bank),
+                               K, _ptr(u), _ptr(cost), _ptr(idx), _ptr(costs), stream))
+    ms = last_kernel_ms() if time_kernel and E > 0 else None
+    return MpcResult(u, cost, idx, costs, ms)

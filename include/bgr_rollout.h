@@ -1,0 +1,314 @@
+/*
+ * bgr_rollout.h -- C ABI of the B200-native batched closed-loop rollout engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of grimgrimberg/BGR_PathPlanning_Control that
+ * this library replaces: tracking law -> bicycle-model step -> lap-metric accumulation, for many
+ * independent episodes at once.  The reference has no FFI of its own (it is
+ * 100 % Python, duck typed); each entry point below names the reference
+ * interface it stands in for.  INTEGRATION.md shows the ctypes binding a reference maintainer adds.
+ *
+ * Conventions
+ *   - every function returns an int status: BGR_OK (0) or a negative BGR_ERR_*; nothing throws
+ *     across the ABI; bgr_last_error_string() describes the last failure on the calling thread.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensors); pointers named
+ *     h_* are HOST pointers.  The library allocates nothing it does not free (stream ordered) before
+ *     returning, except the opaque track handle.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are asynchronous on
+ *     that stream unless the name ends in _host (those synchronise the stream before returning).
+ *   - handles are immutable after creation; concurrent calls on different streams are allowed.
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef BGR_ROLLOUT_H_
+#define BGR_ROLLOUT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden: only this ABI is exported */
+#endif
+
+#define BGR_ABI_VERSION 1
+
+/* ---- status codes ---- */
+#define BGR_OK 0
+#define BGR_ERR_BAD_ARG (-1)
+#define BGR_ERR_CUDA (-2)
+#define BGR_ERR_TOO_LARGE (-3)   /* track does not fit the shared-memory staging budget */
+#define BGR_ERR_ALLOC (-4)
+#define BGR_ERR_UNSUPPORTED (-5)
+
+/* ---- law / model selectors (reference classes they stand for) ---- */
+#define BGR_STEER_PURE_PURSUIT 0 /* PurePursuitController.compute_steering  core/controllers.py:193-230 */
+#define BGR_STEER_STANLEY 1      /* StanleyController.compute_steering (live def) core/controllers.py:336-385 */
+#define BGR_ACCEL_PID 0          /* AccelerationPIDController.compute_acceleration core/controllers.py:32-47 */
+#define BGR_ACCEL_LQG 1          /* LQGAccelerationController.compute_acceleration core/controllers.py:117-138 */
+#define BGR_MODEL_KINEMATIC 0    /* oracle-defined rear-axle kinematic bicycle (no reference code) */
+#define BGR_MODEL_DYNAMIC 1      /* DynamicBicycleModel.state_equations core/data/car_state.py:178-223 */
+#define BGR_PRECISION_FP32 0     /* production: fp32 laws, fp64 integrators for x, y, yaw, v */
+#define BGR_PRECISION_FP64 1     /* audit mode: every operation in fp64, reference operation order */
+
+/* ---- per-episode parameter row: float32[BGR_N_PARAMS] (defaults = vehicle_config.py:4-39) ---- */
+#define BGR_P_LF 0            /* LOOKAHEAD_DISTANCE      vehicle_config.py:37 */
+#define BGR_P_KP 1            /* kp_accel                :19 */
+#define BGR_P_KI 2            /* ki_accel                :20 */
+#define BGR_P_KD 3            /* kd_accel                :21 */
+#define BGR_P_TARGET_SPEED 4  /* TARGET_SPEED            :14 */
+#define BGR_P_K_EXPO 5        /* k_expo                  :24 */
+#define BGR_P_K_STANLEY 6     /* StanleyController.k      core/controllers.py:325,585 */
+#define BGR_P_K_SOFT 7        /* StanleyController.k_soft core/controllers.py:325,585 */
+#define BGR_P_MU 8            /* mu                      vehicle_config.py:13 */
+#define BGR_P_C_F 9           /* c_f                     :11 */
+#define BGR_P_C_R 10          /* c_r                     :12 */
+#define BGR_P_MASS 11         /* m                       :7 */
+#define BGR_P_I_Z 12          /* I_z                     :8 */
+#define BGR_N_PARAMS 16       /* 13..15 reserved (must be 0); rows are 64 B = one 512-bit line */
+
+/* ---- per-episode vehicle state row: double[BGR_N_STATE]  (State, core/data/car_state.py:103-110) ---- */
+#define BGR_X 0
+#define BGR_Y 1
+#define BGR_YAW 2
+#define BGR_V 3
+#define BGR_R 4
+#define BGR_BETA 5
+#define BGR_N_STATE 6
+
+/* ---- per-episode metric row: float32[BGR_N_METRICS]
+ *      (preformance_analysis/metrics_calculator.py:1-8 over the rows of simulation_logger.py:8-10) ---- */
+#define BGR_M_LAT_MEAN 0   /* calculate_lateral_error()[0] */
+#define BGR_M_LAT_STD 1    /* calculate_lateral_error()[1]  (pandas std, ddof = 1; NaN for one row) */
+#define BGR_M_HEAD_MEAN 2  /* calculate_heading_error()[0] */
+#define BGR_M_HEAD_STD 3   /* calculate_heading_error()[1] */
+#define BGR_M_LAP_TIME 4   /* calculate_lap_time(): (rows - 1) * dt */
+#define BGR_M_MAX_ABS_LAT 5
+#define BGR_M_X 6          /* final state, rounded to float32 */
+#define BGR_M_Y 7
+#define BGR_M_YAW 8
+#define BGR_M_V 9
+#define BGR_M_R 10
+#define BGR_M_BETA 11
+#define BGR_N_METRICS 12
+
+/* ---- per-episode status row: int32[BGR_N_STATUS] ---- */
+#define BGR_S_FLAGS 0        /* BGR_ST_* bits */
+#define BGR_S_STEPS 1        /* logged rows == executed steps */
+#define BGR_S_TARGET_IND 2   /* final target index (PP: on the unrolled path) */
+#define BGR_S_NEAREST_IND 3  /* final nearest index on the base lap */
+#define BGR_S_CONE_HITS 4    /* distinct cones hit */
+#define BGR_S_LAPS 5
+#define BGR_S_NEAR_TIES 6    /* steps with a threshold decision closer than tie_eps (audit channel) */
+#define BGR_S_FIRST_TIE 7    /* first such step, -1 if none */
+#define BGR_S_FALLBACKS 8    /* steps that needed the exact global nearest scan */
+#define BGR_N_STATUS 10
+
+#define BGR_ST_PATH_END 1
+#define BGR_ST_LAPS_DONE 2
+#define BGR_ST_TIMEOUT 4
+#define BGR_ST_NONFINITE 8
+
+/* ---- optional per-step trajectory dump row: double[BGR_N_TRAJ], layout [episode][step][field] ---- */
+#define BGR_T_X 0
+#define BGR_T_Y 1
+#define BGR_T_YAW 2
+#define BGR_T_V 3
+#define BGR_T_R 4
+#define BGR_T_BETA 5
+#define BGR_T_STEER 6
+#define BGR_T_ACCEL 7
+#define BGR_T_TARGET_IND 8
+#define BGR_T_NEAREST_IND 9
+#define BGR_T_E_CT 10
+#define BGR_T_THETA_E 11
+#define BGR_N_TRAJ 12
+
+/* ---- per-device aggregate row: double[BGR_N_AGG] (fixed-order reduction over the call's episodes) ---- */
+#define BGR_A_EPISODES 0
+#define BGR_A_STEPS 1
+#define BGR_A_SUM_LAT_MEAN 2
+#define BGR_A_SUM_LAT_STD 3
+#define BGR_A_SUM_LAP_TIME 4
+#define BGR_A_MIN_LAP_TIME 5
+#define BGR_A_CONE_HITS 6
+#define BGR_A_FINISHED 7     /* episodes with PATH_END or LAPS_DONE */
+#define BGR_N_AGG 8
+
+typedef struct bgr_track bgr_track_t; /* opaque, device resident */
+
+/* Centreline + cones as the reference's controllers receive them: cx, cy (nodes/planner.py:88) and
+ * curve (nodes/planner.py:89), all float64 host arrays of length n (the BASE LAP; must not repeat
+ * the first point at the end when closed). */
+typedef struct bgr_track_desc {
+  const double* h_x;
+  const double* h_y;
+  const double* h_kappa;
+  int32_t n;
+  int32_t closed;          /* 1: nearest search and lap counter wrap around; 0: open path */
+  const double* h_cones_xy; /* interleaved x, y; may be NULL */
+  int32_t n_cones;
+  int32_t reserved;
+  double cone_reach;       /* cones within cone_reach of a waypoint are that waypoint's candidates;
+                              must be >= hit_radius + 6 * sigma_cone * sqrt(2) + BGR_CONE_GUARD */
+} bgr_track_desc_t;
+#define BGR_CONE_GUARD 2.0 /* [m] car-to-nearest-waypoint distance up to which candidate lists are exact */
+#define BGR_MAX_CONES 512
+
+typedef struct bgr_track_info {
+  int32_t n, closed, n_cones, device;
+  int64_t smem_bytes_fp32, smem_bytes_fp64;
+  double guard_min, guard_median; /* exactness-guard radii of the windowed nearest search [m] */
+  double ds_min, ds_max;          /* waypoint spacing [m] */
+} bgr_track_info_t;
+
+#define BGR_CFG_AUDIT 1 /* run the full kernel build so that the near-tie audit channel
+                           (BGR_S_NEAR_TIES / BGR_S_FIRST_TIE) is filled even without cones/noise/traj */
+
+typedef struct bgr_rollout_cfg {
+  int32_t steer_kind, accel_kind, model_kind, precision;
+  int32_t max_steps;       /* step cap (legacy loop: T / dt, old/animation_loop.py:16-17,71) */
+  int32_t laps;            /* PP: base lap tiled this many times (monotone index, no wrap) */
+  int32_t laps_target;     /* stop after this many completed laps; 0 = off */
+  int32_t flags;           /* BGR_CFG_* bits */
+  double dt;               /* vehicle_config.py:39 */
+  double wheelbase;        /* WB = l_f + l_r, vehicle_config.py:16 */
+  double l_f, l_r;         /* :9-10 */
+  double max_steer;        /* :35 */
+  double max_accel;        /* :30 */
+  double max_decel;        /* :31 (negative) */
+  double hit_radius;       /* 0 = cone hits off */
+  double tie_eps;          /* [m] near-tie audit threshold; 0 = default 2e-5 */
+  /* observation noise (config 5); all sigmas 0 = off.  Philox4x32-10, key = (seed, episode id) */
+  double sigma_xy, sigma_yaw, sigma_v, sigma_cone;
+  uint32_t noise_seed;
+  uint32_t reserved1;
+  int64_t episode_id_base; /* global id of episode 0 of this call (multi-GPU shards) */
+} bgr_rollout_cfg_t;
+
+typedef struct bgr_mpc_cfg {
+  int32_t horizon;         /* MPCController.N  core/controllers.py:472,587 */
+  int32_t precision;
+  double dt;               /* MPCController.dt */
+  double wheelbase;        /* conf.WB, :525 */
+  double target_speed;     /* conf.TARGET_SPEED, :540 */
+  double q[4];             /* diag Q :483 */
+  double r[2];             /* diag R :484 */
+  double max_accel, max_decel, max_steer; /* :565-566 */
+} bgr_mpc_cfg_t;
+
+/* ---- library ---- */
+int bgr_abi_version(void);
+const char* bgr_last_error_string(void);
+int bgr_device_count(int* out_count);
+
+/* ---- track handle: replaces the (N,3) `path` ndarray + `curve` the reference hands its controllers
+ *      every call (nodes/controller.py:56,62) ---- */
+int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_track_t** out_track);
+void bgr_track_destroy(bgr_track_t* track);
+int bgr_track_info(const bgr_track_t* track, bgr_track_info_t* out_info);
+/* host copies of derived per-waypoint tables, each double[n]: path heading (core/controllers.py:361-368)
+ * and the exactness-guard radius of the nearest search. */
+int bgr_track_tables(const bgr_track_t* track, double* h_path_yaw, double* h_guard_radius);
+
+/* ---- batched closed-loop rollout: replaces the per-step Python loop
+ *      Controller.update (nodes/controller.py:28-94) / old/animation_loop.py:71-136
+ *      + State.update (core/data/car_state.py:118-125) + metrics_calculator (:1-8). ---- */
+int bgr_rollout(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
+                const float* d_params,      /* [n_episodes][BGR_N_PARAMS] */
+                const double* d_init_state, /* [n_episodes][BGR_N_STATE] */
+                float* d_metrics,           /* [n_episodes][BGR_N_METRICS] */
+                int32_t* d_status,          /* [n_episodes][BGR_N_STATUS] */
+                double* d_traj,             /* NULL or [n_episodes][max_steps][BGR_N_TRAJ] */
+                double* d_aggregate,        /* NULL or [BGR_N_AGG] */
+                void* stream);
+
+/* Same call with HOST buffers: H2D of params/init, the rollout, D2H of metrics/status/aggregate, and a
+ * stream synchronise, all inside.  This is what a reference-side caller holding numpy arrays uses. */
+int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
+                     const float* h_params, const double* h_init_state, float* h_metrics,
+                     int32_t* h_status, double* h_traj, double* h_aggregate, void* stream);
+
+/* ---- one control step for n independent vehicles (the scalar drop-in classes call this with n = 1):
+ *      compute_steering (core/controllers.py:193 / :336), curvature lookup (nodes/controller.py:62),
+ *      compute_acceleration (:32 / :117), State.update (core/data/car_state.py:118).
+ *      `phases` selects what runs: BGR_PHASE_*.  HOST pointers; synchronous. ---- */
+#define BGR_PHASE_STEER 1
+#define BGR_PHASE_ACCEL 2
+#define BGR_PHASE_MODEL 4
+#define BGR_PHASE_ERRORS 8
+#define BGR_PHASE_KAPPA_GIVEN 16 /* curvature comes from h_cmd[.][BGR_CMD_KAPPA], not from the lookup:
+                                    compute_acceleration(current_speed, curvature) takes it as an argument */
+/* command row: double[BGR_N_CMD] */
+#define BGR_CMD_STEER 0
+#define BGR_CMD_ACCEL 1
+#define BGR_CMD_KAPPA 2
+#define BGR_N_CMD 4
+/* controller memory row: double[BGR_N_CTRL] */
+#define BGR_C_PID_INTEGRAL 0
+#define BGR_C_PID_LAST_INPUT 1
+#define BGR_C_PID_HAS_LAST 2
+#define BGR_C_LQG_XHAT0 3
+#define BGR_C_LQG_XHAT1 4
+#define BGR_C_LQG_A_PREV 5
+#define BGR_C_STEP 6         /* LQG: index into the shared Kalman-gain sequence */
+#define BGR_N_CTRL 8
+/* step output row: double[BGR_N_OUT] */
+#define BGR_O_STEER 0
+#define BGR_O_ACCEL 1
+#define BGR_O_V_DESIRED 2    /* .maxspeed (PID, nodes/controller.py:71) / .v_desired (LQG) */
+#define BGR_O_KAPPA 3
+#define BGR_O_E_CT 4
+#define BGR_O_THETA_E 5
+#define BGR_O_NEAREST_IND 6
+#define BGR_N_OUT 8
+int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int32_t phases, int64_t n,
+                  const float* h_params,   /* [n][BGR_N_PARAMS] */
+                  double* h_state,         /* [n][BGR_N_STATE] in/out (out only if BGR_PHASE_MODEL) */
+                  int32_t* h_target_ind,   /* [n] in/out */
+                  double* h_ctrl,          /* [n][BGR_N_CTRL] in/out */
+                  const double* h_cmd,     /* NULL, or [n][BGR_N_CMD]: (steer, accel) commands to use for the
+                                              phases that are switched off, and the given curvature */
+                  double* h_out,           /* [n][BGR_N_OUT] */
+                  void* stream);
+
+/* ---- LQG design shared by all episodes: LQR gain (control.dlqr call, core/controllers.py:97) and the
+ *      data-independent Kalman gain sequence (:145,151,154,160).  Host math, no device work. ---- */
+int bgr_lqg_design(double dt, int32_t n_steps, double* h_lqr_gain /*[2]*/, double* h_kf_gains /*[n_steps][2] or NULL*/);
+
+/* ---- MPC candidate-sequence rollout + cost evaluation: replaces the cvxpy/OSQP solve inside
+ *      MPCController.compute_control (core/controllers.py:486-568) by evaluating the reference's own
+ *      cost (:545,:548) under its linearised dynamics (:522-527) for K candidate control sequences
+ *      per episode and taking the cheapest feasible (:536) one. ---- */
+int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                 const double* d_state,      /* [n_episodes][4] = x, y, yaw, v */
+                 const int32_t* d_ref_start, /* [n_episodes] first reference waypoint (path[0] of :499-500) */
+                 const int32_t* d_ref_len,   /* NULL (= path runs to the end of the base lap) or [n_episodes] */
+                 const float* d_bank,        /* [K][horizon][2] = (accel, steer) candidate bank */
+                 int32_t n_candidates,
+                 float* d_best_u,            /* [n_episodes][2] = (acceleration, steering) as returned at :568 */
+                 float* d_best_cost,         /* [n_episodes]; +inf when no candidate is feasible */
+                 int32_t* d_best_idx,        /* [n_episodes]; -1 when none feasible */
+                 float* d_costs,             /* NULL or [n_episodes][K] (+inf = infeasible) */
+                 void* stream);
+int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                      const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
+                      const float* h_bank, int32_t n_candidates, float* h_best_u, float* h_best_cost,
+                      int32_t* h_best_idx, float* h_costs, void* stream);
+
+/* ---- measurement helpers ---- */
+/* FP32 FMA-chain microbenchmark: the roofline denominator for the step kernels (MEASURED_PEAKS.json has
+ * only HBM and bf16).  Returns achieved TFLOP/s (2 flops per FMA) and lane-instructions/s. */
+int bgr_fp32_peak_probe(int device, double* out_tflops, double* out_ginst_per_s);
+/* Duration [ms] of the last rollout / mpc kernel launched by this thread on `stream`, measured with
+ * CUDA events recorded on that stream around the kernel (synchronises the stream). */
+int bgr_last_kernel_ms(double* out_ms);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t bgr_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGR_ROLLOUT_H_ */
