@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- closed-loop sim-steps/sec of the batched rollout engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload pp_sweep|stanley_lqg|mpc]
+
+A "step" is ONE pass of the hot path over one batch of synthetic input: one ``bgr_rollout`` of E episodes x S
+closed-loop control steps (default workload = BASELINE config 2: the pure-pursuit look-ahead / PID-gain sweep,
+E = 1 Mi episodes x S = 2 000 steps per GPU on the stadium-oval Trackdrive centreline, kinematic bicycle).
+``value`` = sim-steps actually executed by all ranks / max-over-ranks device time, inputs resident in HBM.
+``e2e`` = the same through the host-buffer C-ABI call (``bgr_rollout_host``: pinned numpy in, numpy out, H2D and
+D2H inside the timed region).  Multi-GPU: one process per GPU (torchrun), episodes sharded, NO data-path
+collective (scaling: weak); the final metric gather + aggregate reduction (NCCL) is timed separately.
+
+``--impl reference`` times the CPU arm: the reference's own Python functions as composed by oracle/loop.py
+(the reference is 100 % Python and cannot be installed on the GPU box -- see DESIGN.md), on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "closed-loop sim-steps/sec (episodes x steps)"
+UNIT = "sim-steps/s"
+
+WORKLOADS = {
+    # name: (steer, accel, model, laps of the unrolled path, BASELINE config it is)
+    "pp_sweep": ("pure_pursuit", "pid", "kinematic", 8,
+                 "config 2: pure-pursuit lookahead/gain sweep, 1Mi episodes x 2000 steps, stadium oval N=1024, 1 B200"),
+    "stanley_lqg": ("stanley", "lqg", "dynamic", 1,
+                    "config 3: Stanley + LQG + dynamic bicycle (tyre slip), episodes sharded over the GPUs"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pp_sweep", choices=list(WORKLOADS) + ["mpc"])
+    ap.add_argument("--episodes", type=int, default=1 << 20, help="episodes per GPU per step")
+    ap.add_argument("--sim-steps", type=int, default=2000, help="closed-loop control steps per episode")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle loop (reference functions composed; test infrastructure) on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    workload, start, count, sim_steps = job
+    import bgr_pathplanning_control_b200 as bgr
+    from oracle import loop
+    steer, accel, model, laps, _ = WORKLOADS[workload]
+    ta = bgr.tracks.stadium_oval(1024)
+    track = loop.Track(ta.x, ta.y, ta.kappa, True, ta.cones)
+    params = (bgr.sweeps.pp_sweep_params(count, start) if workload == "pp_sweep"
+              else bgr.sweeps.stanley_lqg_params(count, start=start))
+    init = bgr.initial_states(ta, count)
+    spec = loop.RolloutSpec(steer=steer, accel=accel, model=model, max_steps=sim_steps, laps=laps)
+    done = 0
+    t0 = time.perf_counter()
+    for e in range(count):
+        out = loop.rollout_episode(track, spec, params[e].astype(np.float64), init[e], record=False)
+        done += out["steps"]
+    return done, time.perf_counter() - t0
+
+
+def cpu_sample(workload, sim_steps, seconds, cores=None):
+    """Run a bounded sample of the workload's episodes through the oracle loop on ``cores`` processes.
+    Returns (steps/s aggregate, cores, description)."""
+    import multiprocessing as mp
+    cores = cores or len(os.sched_getaffinity(0))
+    # calibrate on one short episode (in this process), then size the sample for ~`seconds`
+    done, dt = _cpu_worker((workload, 0, 1, min(sim_steps, 400)))
+    rate1 = done / dt
+    per_core = max(1, int(rate1 * seconds / sim_steps))
+    per_core = min(per_core, 64)
+    jobs = [(workload, 4099 * c, per_core, sim_steps) for c in range(cores)]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    desc = (f"{cores} processes x {per_core} episodes x {sim_steps} steps of the same sweep rows "
+            f"(oracle/loop.py: reference functions in the order of nodes/controller.py:61-63), "
+            f"{total} sim-steps in {busy:.1f} s (pool wall {wall:.1f} s)")
+    return total / busy, cores, desc
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    """`--impl reference`: rank 0 alone times the CPU path; the other ranks exit 0 without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    workload = args.workload if args.workload in WORKLOADS else "pp_sweep"
+    per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(workload, min(args.sim_steps, 200), 0.5)
+    vals, descs, t_total, steps_total = [], [], 0.0, 0
+    cores = len(os.sched_getaffinity(0))
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        v, cores, desc = cpu_sample(workload, args.sim_steps, per_step)
+        vals.append(v)
+        descs.append(desc)
+        t_total += time.perf_counter() - t0
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[workload][4], "episodes_per_gpu": args.episodes, "sim_steps": args.sim_steps,
+                   "note": "CPU arm: each step is a bounded sample of the workload's episodes, all host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": descs[-1],
+                         "cpu": cpu_model()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import bgr_pathplanning_control_b200 as bgr
+    from bgr_pathplanning_control_b200 import _abi as abi
+    from bgr_pathplanning_control_b200 import roofline as rf
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "mpc":
+        return run_mpc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, barrier)
+
+    steer, accel, model, laps, desc = WORKLOADS[args.workload]
+    E, S = args.episodes, args.sim_steps
+    ta = bgr.tracks.stadium_oval(1024)
+    track = bgr.Track.from_arrays(ta, device=local)
+    cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=laps,
+                            episode_id_base=rank * E)
+    # Input sets: each timed step consumes a DIFFERENT batch (rows of the sweep grid shifted by rank and set), so
+    # the inputs touched over the timed region (n_sets x 112 B x E) exceed the 126 MB L2.
+    n_sets = 4
+    make = bgr.sweeps.pp_sweep_params if args.workload == "pp_sweep" else \
+        (lambda n, start: bgr.sweeps.stanley_lqg_params(n, start=start))
+    h_params = [torch.from_numpy(make(E, (rank * n_sets + s) * 65537)).pin_memory() for s in range(n_sets)]
+    h_init = [torch.from_numpy(bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.2, 0.2, E) * (s % 2)))
+              .pin_memory() for s in range(n_sets)]
+    d_params = [t.to(dev) for t in h_params]
+    d_init = [t.to(dev) for t in h_init]
+    out = bgr.RolloutResult(torch.empty((E, abi.N_METRICS), dtype=torch.float32, device=dev),
+                            torch.empty((E, abi.N_STATUS), dtype=torch.int32, device=dev), None,
+                            torch.empty(abi.N_AGG, dtype=torch.float64, device=dev))
+
+    def step(i):
+        return bgr.rollout(track, cfg, d_params[i % n_sets], d_init[i % n_sets], aggregate=True, out=out)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = bgr.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    steps_done = torch.zeros((), dtype=torch.float64, device=dev)
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        r = step(i)
+        ev[i][1].record()
+        steps_done += r.aggregate[abi.A_STEPS]
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = bgr.launch_count() - launches0
+    ms_total = t_begin.elapsed_time(t_end)
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    kernel_ms_last = bgr.last_kernel_ms()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    tot = steps_done.clone().reshape(1)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    total_sim_steps = float(tot.item())
+    value = total_sim_steps / (ms_total * 1e-3)
+
+    # ---- final metric gather + aggregate reduction: the ONLY cross-rank traffic (timed separately) ----
+    gather_ms = None
+    if world > 1:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        m_all, s_all, agg_all = bgr.sharding.gather_results(out.metrics, out.status, out.aggregate, E * world)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
+        assert m_all.shape[0] == E * world and float(agg_all[abi.A_EPISODES]) == E * world
+
+    # ---- e2e: host buffers through bgr_rollout_host (H2D + kernel + D2H inside the timed region) ----
+    np_params = [t.numpy() for t in h_params]
+    np_init = [t.numpy() for t in h_init]
+    h_out = bgr.RolloutResult(torch.empty((E, abi.N_METRICS), dtype=torch.float32).pin_memory().numpy(),
+                              torch.empty((E, abi.N_STATUS), dtype=torch.int32).pin_memory().numpy())
+    for i in range(min(args.warmup, 2)):
+        bgr.rollout(track, cfg, np_params[i % n_sets], np_init[i % n_sets], aggregate=True, out=h_out)
+    barrier()
+    e2e_steps = 0.0
+    w0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        r = bgr.rollout(track, cfg, np_params[i % n_sets], np_init[i % n_sets], aggregate=True, out=h_out)
+        e2e_steps += float(r.aggregate[abi.A_STEPS])
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    e2e_value = float(tot.item()) / (float(t.item()) * 1e-3)
+    h2d = E * (abi.N_PARAMS * 4 + abi.N_STATE * 8)
+    d2h = E * (abi.N_METRICS * 4 + abi.N_STATUS * 4) + abi.N_AGG * 8
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        fp32_tflops, fp32_ginst = bgr.fp32_peak_probe(local)
+        flops_step = rf.flops_per_step(steer, accel, model)
+        k_ms = float(np.mean(kernel_ms))
+        steps_per_launch = total_sim_steps / world / args.steps
+        achieved_tflops = steps_per_launch * flops_step / (k_ms * 1e-3) / 1e12
+        bytes_launch = E * rf.bytes_per_episode()
+        hbm_gbs = bytes_launch / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 laws + f64 integrators (x, y, yaw, v) and metric sums", "data": "synthetic",
+            "config": {"workload": desc, "episodes_per_gpu": E, "sim_steps": S, "steer": steer, "accel": accel,
+                       "model": model, "track": "stadium_oval n=1024", "parallelism": f"episode sharding x{world}",
+                       "l2": f"{n_sets} rotating input sets ({n_sets * h2d / 1e6:.0f} MB) > 126 MB L2, no flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "bgr_rollout_host (pinned numpy in, numpy out)"},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_tflops, "unit": "TFLOP/s",
+                "frac": achieved_tflops / fp32_tflops, "traffic": None,
+                "peak_source": "bgr_fp32_peak_probe (FFMA chains, measured in this run); MEASURED_PEAKS.json has no fp32 row",
+                "flops_per_sim_step": flops_step, "kernel_ms_avg": k_ms, "kernel_ms_last": kernel_ms_last,
+                "sim_steps_per_launch": steps_per_launch,
+                "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
+                        "bytes_per_launch": bytes_launch, "peak_source": peaks_src},
+            },
+        }
+        if gather_ms is not None:
+            line["gather_ms"] = gather_ms
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_sample(args.workload, S, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "cpu": cpu_model()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_mpc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, barrier):
+    """BASELINE config 4 (secondary bench line): 16k episodes x 4096 candidates x horizon 30."""
+    E, K, H = 16384, 4096, 30
+    ta = bgr.tracks.stadium_oval(1024)
+    track = bgr.Track.from_arrays(ta, device=local)
+    cfg = bgr.MpcConfig(horizon=H, dt=0.05)
+    states, ref_start = bgr.sweeps.mpc_states(ta, E, start=rank * E)
+    bank = bgr.candidate_bank(K, H)
+    d_state, d_ref, d_bank = (torch.from_numpy(a).to(dev) for a in (states, ref_start, bank))
+    for _ in range(args.warmup):
+        bgr.mpc_evaluate(track, cfg, d_state, d_ref, d_bank)
+    barrier()
+    launches0 = bgr.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        res = bgr.mpc_evaluate(track, cfg, d_state, d_ref, d_bank)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    kernel_ms = bgr.last_kernel_ms()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    units = float(E) * K * H * world * args.steps
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        bgr.mpc_evaluate(track, cfg, states, ref_start, bank)
+    e2e_s = time.perf_counter() - w0
+    if rank == 0:
+        fp32_tflops, _ = bgr.fp32_peak_probe(local)
+        ach = float(E) * K * H * rf.FLOPS["mpc_candidate_step"] / (kernel_ms * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "MPC candidate-steps/sec (episodes x candidates x horizon)", "value": units / (ms * 1e-3),
+            "unit": "candidate-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config 4: MPC candidate-sequence rollout/cost evaluation, 16384 episodes x 4096 "
+                                   "candidates x horizon 30", "solves_per_s": E * world * args.steps / (ms * 1e-3)},
+            "e2e": {"value": float(E) * K * H * args.steps / e2e_s, "unit": "candidate-steps/s",
+                    "h2d_bytes_per_step": states.nbytes + ref_start.nbytes + bank.nbytes, "d2h_bytes_per_step": E * 16},
+            "gpu_launches": int(bgr.launch_count() - launches0),
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_tflops, "unit": "TFLOP/s",
+                         "frac": ach / fp32_tflops, "traffic": None, "kernel_ms_last": kernel_ms},
+        }), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -94,7 +94,7 @@ class State:
                          float(self.beta)]])
         cmd = np.zeros((1, abi.N_CMD))
         cmd[0, abi.CMD_STEER], cmd[0, abi.CMD_ACCEL] = float(delta), float(a)
-        _step(_dummy_track(), cfg, abi.PHASE_MODEL, engine.default_params(1), row, 0, None, cmd)
+        _step(_dummy_track(), cfg, abi.PHASE_MODEL, engine.default_params(1, np.float64), row, 0, None, cmd)
         self.x, self.y, self.yaw, self.v, self.r, self.beta = (float(v) for v in row[0])
         self.update_positions()
 

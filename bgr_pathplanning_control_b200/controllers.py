@@ -95,7 +95,7 @@ class PurePursuitController:
         """-> (steering [rad] as np.float64, target index as int)   (:193-230)"""
         cx, cy = _path_columns(path)
         track = _track_for(cx, cy)
-        params = engine.default_params(1)
+        params = engine.default_params(1, np.float64)
         params[0, abi.P_LF] = self.look_ahead_distance
         cfg = engine.RolloutConfig(steer="pure_pursuit", precision="fp64")
         out, ti = _step(track, cfg, abi.PHASE_STEER, params, _state_row(state), target_ind,
@@ -114,7 +114,7 @@ class StanleyController:
         """-> (steering as np.float64, nearest index as np.int64); ``target_ind`` is ignored (:356)."""
         cx, cy = _path_columns(path)
         track = _track_for(cx, cy)
-        params = engine.default_params(1)
+        params = engine.default_params(1, np.float64)
         params[0, abi.P_K_STANLEY], params[0, abi.P_K_SOFT] = self.k, self.k_soft
         cfg = engine.RolloutConfig(steer="stanley", precision="fp64")
         out, ti = _step(track, cfg, abi.PHASE_STEER | abi.PHASE_ERRORS, params, _state_row(state), 0,
@@ -132,7 +132,7 @@ class AccelerationPIDController:
         self._ctrl = np.zeros((1, abi.N_CTRL))
 
     def compute_acceleration(self, current_speed, curvature):
-        params = engine.default_params(1)
+        params = engine.default_params(1, np.float64)
         params[0, abi.P_KP], params[0, abi.P_KI], params[0, abi.P_KD] = self.kp, self.ki, self.kd
         cfg = engine.RolloutConfig(accel="pid", precision="fp64")
         state = np.zeros((1, abi.N_STATE))
@@ -145,7 +145,7 @@ class AccelerationPIDController:
 
     def compute_breaking(self, curvature):
         """Desired speed for a curvature (:58-73), evaluated by the same kernel (no state change)."""
-        params = engine.default_params(1)
+        params = engine.default_params(1, np.float64)
         cfg = engine.RolloutConfig(accel="pid", precision="fp64")
         cmd = np.zeros((1, abi.N_CMD))
         cmd[0, abi.CMD_KAPPA] = float(curvature)
@@ -170,7 +170,7 @@ class LQGAccelerationController:
         return self._ctrl[0, abi.C_LQG_XHAT0:abi.C_LQG_XHAT1 + 1].reshape(2, 1).copy()
 
     def compute_acceleration(self, current_speed, curvature):
-        params = engine.default_params(1)
+        params = engine.default_params(1, np.float64)
         cfg = engine.RolloutConfig(accel="lqg", precision="fp64", dt=self.dt)
         state = np.zeros((1, abi.N_STATE))
         state[0, abi.V] = float(current_speed)
@@ -232,7 +232,7 @@ def find_target_point(state, cx, cy, target_ind):
     """core/controllers.py:605-612: the look-ahead scan with ``conf.LOOKAHEAD_DISTANCE``, capped at
     ``len(cx) - 1`` -- the same device scan as pure pursuit."""
     track = _track_for(cx, cy)
-    params = engine.default_params(1)
+    params = engine.default_params(1, np.float64)
     cfg = engine.RolloutConfig(steer="pure_pursuit", precision="fp64")
     _, ti = _step(track, cfg, abi.PHASE_STEER, params, _state_row(state), target_ind, cmd=np.zeros((1, abi.N_CMD)))
     return ti

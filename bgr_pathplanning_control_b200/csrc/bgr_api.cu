@@ -469,6 +469,7 @@ struct StepPlumbing {
   int32_t* ti_out = nullptr;
   double* state_out = nullptr;
   const double* cmd = nullptr;
+  const double* params64 = nullptr;
   double* step_out = nullptr;
   bool force_full = false;
 };
@@ -541,7 +542,8 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
     }
     return BGR_OK;
   }
-  if (d_params == nullptr || d_init == nullptr || d_metrics == nullptr || d_status == nullptr) {
+  if ((d_params == nullptr && sp.params64 == nullptr) || d_init == nullptr || d_metrics == nullptr ||
+      d_status == nullptr) {
     set_error("bgr_rollout: d_params / d_init_state / d_metrics / d_status is NULL");
     return BGR_ERR_BAD_ARG;
   }
@@ -611,6 +613,7 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   A.ti_out = sp.ti_out;
   A.state_out = sp.state_out;
   A.cmd = sp.cmd;
+  A.params64 = sp.params64;
   A.step_out = sp.step_out;
 
   const int grid = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
@@ -763,7 +766,7 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
 }
 
 extern "C" int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg_in, int32_t phases, int64_t n,
-                             const float* h_params, double* h_state, int32_t* h_target_ind, double* h_ctrl,
+                             const double* h_params, double* h_state, int32_t* h_target_ind, double* h_ctrl,
                              const double* h_cmd, double* h_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BGR_TRY(validate_cfg(track, cfg_in, "bgr_step_host"));
@@ -787,7 +790,7 @@ extern "C" int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* 
   DeviceScope dev(track->device);
   Scratch sc(stream);
   const size_t E = static_cast<size_t>(n);
-  float* d_params;
+  double* d_params;
   double *d_state, *d_state_out, *d_ctrl_in, *d_ctrl_out, *d_cmd = nullptr, *d_out;
   float* d_metrics;
   int32_t *d_status, *d_ti_in, *d_ti_out;
@@ -801,7 +804,7 @@ extern "C" int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* 
   BGR_TRY(sc.get(&d_status, E * BGR_N_STATUS));
   BGR_TRY(sc.get(&d_ti_in, E));
   BGR_TRY(sc.get(&d_ti_out, E));
-  BGR_CUDA(cudaMemcpyAsync(d_params, h_params, E * BGR_N_PARAMS * sizeof(float), cudaMemcpyHostToDevice, stream));
+  BGR_CUDA(cudaMemcpyAsync(d_params, h_params, E * BGR_N_PARAMS * sizeof(double), cudaMemcpyHostToDevice, stream));
   BGR_CUDA(cudaMemcpyAsync(d_state, h_state, E * BGR_N_STATE * sizeof(double), cudaMemcpyHostToDevice, stream));
   if (h_ctrl != nullptr)
     BGR_CUDA(cudaMemcpyAsync(d_ctrl_in, h_ctrl, E * BGR_N_CTRL * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -824,8 +827,9 @@ extern "C" int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* 
   sp.state_out = d_state_out;
   sp.cmd = d_cmd;
   sp.step_out = d_out;
+  sp.params64 = d_params;
   sp.force_full = true;
-  BGR_TRY(rollout_impl(track, &cfg, n, d_params, d_state, d_metrics, d_status, nullptr, nullptr, sp, stream));
+  BGR_TRY(rollout_impl(track, &cfg, n, nullptr, d_state, d_metrics, d_status, nullptr, nullptr, sp, stream));
   if (phases & BGR_PHASE_MODEL)
     BGR_CUDA(cudaMemcpyAsync(h_state, d_state_out, E * BGR_N_STATE * sizeof(double), cudaMemcpyDeviceToHost, stream));
   if (h_ctrl != nullptr)

@@ -87,6 +87,7 @@ struct RolloutArgs {
   const int32_t* ti_in;    // [E]
   int32_t* ti_out;
   double* state_out;       // [E][BGR_N_STATE] final state in fp64
+  const double* params64;  // [E][BGR_N_PARAMS] fp64 parameter rows (replace `params` when set)
   const double* cmd;       // [E][BGR_N_CMD] (steer, accel, kappa) used for switched-off phases
   double* step_out;        // [E][BGR_N_OUT] outputs of the LAST executed step
 };

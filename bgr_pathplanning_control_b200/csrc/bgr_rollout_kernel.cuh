@@ -51,12 +51,26 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
   const long long er = active ? e : 0;
 
   // ---- per-episode parameters: four coalesced 128-bit loads of the 64 B row ----
-  const float4* prow = reinterpret_cast<const float4*>(A.params) + er * (BGR_N_PARAMS / 4);
-  const float4 q0 = __ldg(prow + 0), q1 = __ldg(prow + 1), q2 = __ldg(prow + 2), q3 = __ldg(prow + 3);
-  const Real Lf = q0.x, kp = q0.y, ki = q0.z, kd = q0.w;
-  const Real tspeed = q1.x, k_expo = q1.y, k_st = q1.z, k_soft = q1.w;
-  const Real mu = q2.x, c_f = q2.y, c_r = q2.z, mass = q2.w;
-  const Real I_z = q3.x;
+  Real Lf, kp, ki, kd, tspeed, k_expo, k_st, k_soft, mu, c_f, c_r, mass, I_z;
+  bool params_f64 = false;
+  if constexpr (EXTRAS) params_f64 = A.params64 != nullptr;
+  if (params_f64) {
+    // single-step drop-in API: the reference's scalars are fp64, keep every bit of them
+    const double* p = A.params64 + er * BGR_N_PARAMS;
+    Lf = static_cast<Real>(p[BGR_P_LF]); kp = static_cast<Real>(p[BGR_P_KP]); ki = static_cast<Real>(p[BGR_P_KI]);
+    kd = static_cast<Real>(p[BGR_P_KD]); tspeed = static_cast<Real>(p[BGR_P_TARGET_SPEED]);
+    k_expo = static_cast<Real>(p[BGR_P_K_EXPO]); k_st = static_cast<Real>(p[BGR_P_K_STANLEY]);
+    k_soft = static_cast<Real>(p[BGR_P_K_SOFT]); mu = static_cast<Real>(p[BGR_P_MU]);
+    c_f = static_cast<Real>(p[BGR_P_C_F]); c_r = static_cast<Real>(p[BGR_P_C_R]);
+    mass = static_cast<Real>(p[BGR_P_MASS]); I_z = static_cast<Real>(p[BGR_P_I_Z]);
+  } else {
+    const float4* prow = reinterpret_cast<const float4*>(A.params) + er * (BGR_N_PARAMS / 4);
+    const float4 q0 = __ldg(prow + 0), q1 = __ldg(prow + 1), q2 = __ldg(prow + 2), q3 = __ldg(prow + 3);
+    Lf = q0.x; kp = q0.y; ki = q0.z; kd = q0.w;
+    tspeed = q1.x; k_expo = q1.y; k_st = q1.z; k_soft = q1.w;
+    mu = q2.x; c_f = q2.y; c_r = q2.z; mass = q2.w;
+    I_z = q3.x;
+  }
 
   const double* irow = A.init + er * BGR_N_STATE;
   double X = __ldg(irow + 0), Y = __ldg(irow + 1), YAW = __ldg(irow + 2), V = __ldg(irow + 3);

@@ -235,7 +235,7 @@ def rollout(track, config, params, init_state, *, traj=False, aggregate=False, o
     lib = abi.load()
     cfg = config.to_struct() if isinstance(config, RolloutConfig) else config
     if isinstance(params, np.ndarray) or isinstance(init_state, np.ndarray):
-        return _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate)
+        return _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out)
     torch = _torch()
     E = int(params.shape[0])
     if not (params.is_cuda and init_state.is_cuda):
@@ -272,13 +272,19 @@ def rollout(track, config, params, init_state, *, traj=False, aggregate=False, o
     return RolloutResult(metrics, status, tr, agg, ms)
 
 
-def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate):
+def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out=None):
     params = _np(params, np.float32)
     E = params.shape[0]
     params = _np(params, np.float32, (E, abi.N_PARAMS))
     init_state = _np(init_state, np.float64, (E, abi.N_STATE))
-    metrics = np.empty((E, abi.N_METRICS), dtype=np.float32)
-    status = np.empty((E, abi.N_STATUS), dtype=np.int32)
+    if out is not None:      # caller-owned (e.g. pinned) result buffers
+        metrics, status = out.metrics, out.status
+        if (metrics.dtype != np.float32 or metrics.shape != (E, abi.N_METRICS) or not metrics.flags.c_contiguous
+                or status.dtype != np.int32 or status.shape != (E, abi.N_STATUS) or not status.flags.c_contiguous):
+            raise ValueError("out.metrics / out.status must be contiguous (E, 12) float32 / (E, 10) int32 arrays")
+    else:
+        metrics = np.empty((E, abi.N_METRICS), dtype=np.float32)
+        status = np.empty((E, abi.N_STATUS), dtype=np.int32)
     tr = np.zeros((E, cfg.max_steps, abi.N_TRAJ)) if traj else None
     agg = np.empty(abi.N_AGG) if aggregate else None
     abi.check(lib.bgr_rollout_host(track.handle, C.byref(cfg), E, _ptr(params), _ptr(init_state), _ptr(metrics),

@@ -262,7 +262,7 @@ int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int
 #define BGR_O_NEAREST_IND 6
 #define BGR_N_OUT 8
 int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int32_t phases, int64_t n,
-                  const float* h_params,   /* [n][BGR_N_PARAMS] */
+                  const double* h_params,  /* [n][BGR_N_PARAMS] -- fp64 rows: the reference's scalars keep every bit */
                   double* h_state,         /* [n][BGR_N_STATE] in/out (out only if BGR_PHASE_MODEL) */
                   int32_t* h_target_ind,   /* [n] in/out */
                   double* h_ctrl,          /* [n][BGR_N_CTRL] in/out */

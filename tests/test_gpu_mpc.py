@@ -1,0 +1,107 @@
+"""MPC candidate-sequence rollout + cost evaluation (``bgr_mpc_eval`` / ``bgr_mpc_eval_host``) against the
+oracle's restatement of the reference's cost and linearised dynamics (core/controllers.py:511-548;
+oracle/laws.py:mpc_costs_batch), same candidate bank on both sides.
+
+Bars: the argmin index is bit-exact wherever the oracle's best and second-best costs differ by more than the
+fp32 resolution of the cost (documented tie rule otherwise: lowest index among equal fp32 costs); costs agree
+to fp32 rounding (rtol 2e-5) in the production build and to 1e-12 in the fp64 audit build; infeasible
+candidates (v < 0 somewhere, :536) are +inf on both sides.
+"""
+import numpy as np
+import pytest
+
+import bgr_pathplanning_control_b200 as bgr
+from bgr_pathplanning_control_b200 import _abi as abi
+from oracle import laws
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_costs(ta, states, ref_start, bank, H, dt):
+    out = np.empty((len(states), len(bank)))
+    for e, s in enumerate(states):
+        idx = (ref_start[e] + np.arange(H)) % ta.n if ta.closed else np.minimum(ref_start[e] + np.arange(H), ta.n - 1)
+        c, f = laws.mpc_costs_batch(s[0], s[1], s[2], s[3], ta.x[idx], ta.y[idx], bank.astype(np.float64), dt)
+        out[e] = np.where(f, c, np.inf)
+    return out
+
+
+@pytest.mark.parametrize("H,K", [(10, 4096), (30, 4096), (17, 1000)])
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_costs_and_argmin(cuda_device, H, K, precision):
+    ta = bgr.tracks.stadium_oval(1024)
+    track = bgr.Track.from_arrays(ta)
+    E = 48
+    states, ref_start = bgr.sweeps.mpc_states(ta, E)
+    states[:4, 3] = [0.02, 0.05, 0.0, 0.1]           # slow cars: many candidates brake below v = 0 -> infeasible
+    bank = bgr.candidate_bank(K, H)
+    cfg = bgr.MpcConfig(horizon=H, dt=0.05, precision=precision)
+    res = bgr.mpc_evaluate(track, cfg, states, ref_start, bank, return_costs=True)
+    want = oracle_costs(ta, states, ref_start, bank, H, 0.05)
+    fin = np.isfinite(want)
+    assert np.array_equal(fin, np.isfinite(res.costs)), "feasibility (v >= 0, :536) must agree exactly"
+    assert (~fin).sum() > 0 and fin.sum() > 0
+    rtol = 2e-5 if precision == "fp32" else 2e-7      # fp64 build still returns float32 costs
+    np.testing.assert_allclose(res.costs[fin], want[fin], rtol=rtol)
+    # argmin: lowest index among the minimal fp32 costs (np.argmin's first-minimum rule)
+    assert np.array_equal(res.best_idx, np.argmin(res.costs, axis=1))
+    assert np.array_equal(res.best_cost, res.costs[np.arange(E), res.best_idx])
+    w32 = want.astype(np.float32)
+    decided = np.array([np.partition(w32[e], 1)[1] > np.partition(w32[e], 1)[0] * (1 + 4 * rtol) for e in range(E)])
+    assert decided.sum() >= E * 3 // 4
+    assert np.array_equal(res.best_idx[decided], np.argmin(want, axis=1)[decided])
+    # return convention of compute_control (:565-568): (clip(accel), -clip(steer)) of the first control
+    for e in range(E):
+        b = res.best_idx[e]
+        _, a, s, _ = laws.mpc_select(np.where(np.arange(K) == b, 0.0, 1.0), np.ones(K, bool), bank.astype(np.float64))
+        assert res.best_u[e, 0] == np.float32(a) and res.best_u[e, 1] == np.float32(s)
+
+
+def test_no_feasible_candidate_is_the_solver_failure_fallback(cuda_device):
+    """All candidates brake a stopped car: (0, 0) and index -1, like the OSQP failure branch (:558-562)."""
+    ta = bgr.tracks.stadium_oval(256)
+    track = bgr.Track.from_arrays(ta)
+    H, K = 10, 64
+    bank = np.zeros((K, H, 2), np.float32)
+    bank[..., 0] = -1.0
+    states = np.array([[0.0, 0.0, 0.0, 0.0]])
+    res = bgr.mpc_evaluate(track, bgr.MpcConfig(horizon=H), states, np.zeros(1, np.int32), bank, return_costs=True)
+    assert res.best_idx[0] == -1 and np.isinf(res.best_cost[0]) and np.all(np.isinf(res.costs))
+    assert res.best_u[0, 0] == 0.0 and res.best_u[0, 1] == 0.0
+
+
+def test_device_tensors_equal_host_buffers_and_open_path_clamps(cuda_device):
+    import torch
+    ta = bgr.tracks.skidpad(512)                     # open path: stage references clamp to the last point (:542)
+    track = bgr.Track.from_arrays(ta)
+    H, K, E = 30, 512, 300
+    states, ref_start = bgr.sweeps.mpc_states(ta, E)
+    ref_start[:5] = ta.n - np.arange(1, 6)           # fewer than H points left
+    bank = bgr.candidate_bank(K, H)
+    cfg = bgr.MpcConfig(horizon=H)
+    host = bgr.mpc_evaluate(track, cfg, states, ref_start, bank, return_costs=True)
+    dev = bgr.mpc_evaluate(track, cfg, torch.from_numpy(states).to(cuda_device),
+                           torch.from_numpy(ref_start).to(cuda_device), torch.from_numpy(bank).to(cuda_device),
+                           return_costs=True)
+    assert np.array_equal(host.costs, dev.costs.cpu().numpy())
+    assert np.array_equal(host.best_idx, dev.best_idx.cpu().numpy())
+    assert np.array_equal(host.best_u, dev.best_u.cpu().numpy())
+    want = oracle_costs(ta, states, ref_start, bank, H, 0.05)
+    fin = np.isfinite(want)
+    assert np.array_equal(fin, np.isfinite(host.costs))
+    np.testing.assert_allclose(host.costs[fin], want[fin], rtol=2e-5)
+
+
+def test_mpc_controller_drop_in(cuda_device):
+    """MPCController.compute_control(state, path) -> (acceleration, steering): reference call convention."""
+    ta = bgr.tracks.stadium_oval(512)
+    path = np.column_stack([np.arange(ta.n), ta.x, ta.y])[100:160]
+    ctrl = bgr.get_steering_controller("mpc")
+    assert ctrl.N == 10 and ctrl.dt == 0.05          # factory values (core/controllers.py:587)
+    st = type("S", (), dict(x=ta.x[100], y=ta.y[100] + 0.2, yaw=0.1, v=4.0))()
+    a, s = ctrl.compute_control(st, path)
+    c, f = laws.mpc_costs_batch(st.x, st.y, st.yaw, st.v, path[:10, 1], path[:10, 2], ctrl.bank.astype(np.float64), 0.05)
+    best, wa, ws, wc = laws.mpc_select(c, f, ctrl.bank.astype(np.float64))
+    assert np.isclose(ctrl.last_cost, wc, rtol=2e-5)
+    assert np.isclose(a, wa, atol=1e-6) and np.isclose(s, ws, atol=1e-6)
+    assert -bgr.conf.MAX_STEER <= s <= bgr.conf.MAX_STEER and bgr.conf.MAX_DECEL <= a <= bgr.conf.MAX_ACCEL

@@ -1,0 +1,292 @@
+"""Parity tests proper: the batched closed-loop rollout (``bgr_rollout`` / ``bgr_rollout_host`` through the C ABI)
+against the fp64 CPU oracle loop (oracle/loop.py = the reference's functions composed in the order of
+nodes/controller.py:61-63) on identical seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * nearest-waypoint / target indices and cone-hit counts: BIT-EXACT, except at documented exact-distance
+    near-ties -- steps where the oracle's own decision margin (|d - Lf| of the look-ahead scan, or runner-up
+    minus winner of the argmin) is below ``TIE_M``; such steps must ALSO be flagged by the kernel's audit channel;
+  * trajectories: 1e-3 m position, 1e-4 rad heading over a full lap (fp32 production kernels vs fp64 oracle);
+  * lap time: 1e-3 s.
+"""
+import numpy as np
+import pytest
+
+import bgr_pathplanning_control_b200 as bgr
+from bgr_pathplanning_control_b200 import _abi as abi
+from oracle import loop
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL, YAW_TOL, LAP_TOL = 1e-3, 1e-4, 1e-3     # north_star tolerances (fp32 GPU vs fp64 reference)
+TIE_M = 2e-5                                     # [m] what counts as an exact-distance near-tie
+
+
+def otrack(ta):
+    return loop.Track(ta.x, ta.y, ta.kappa, ta.closed, ta.cones)
+
+
+def compare(ta, track, cfg, params, init, episodes, *, noise=None, pos_tol=POS_TOL, yaw_tol=YAW_TOL,
+            e_ct_tol=1e-3):
+    """Run the GPU rollout for all rows, the oracle for ``episodes``, and compare step by step."""
+    res = bgr.rollout(track, cfg, params, init, traj=True, aggregate=True)
+    worst = {"pos": 0.0, "yaw": 0.0, "ties": 0}
+    for e in episodes:
+        spec = loop.RolloutSpec(steer=cfg.steer, accel=cfg.accel, model=cfg.model, max_steps=cfg.max_steps,
+                                dt=cfg.dt, laps=cfg.laps, laps_target=cfg.laps_target, hit_radius=cfg.hit_radius,
+                                noise=noise)
+        ref = loop.rollout_episode(otrack(ta), spec, params[e].astype(np.float64), init[e],
+                                   episode_id=cfg.episode_id_base + e)
+        n = ref["steps"]
+        st = res.status[e]
+        tr = res.traj[e, :n]
+        # index parity, with the documented near-tie exemption
+        ti_gpu = tr[:, abi.T_TARGET_IND].astype(np.int64)
+        near_gpu = tr[:, abi.T_NEAREST_IND].astype(np.int64)
+        margin = np.minimum(ref["pp_margin"], ref["near_margin"])
+        bad = np.nonzero((ti_gpu != ref["ti"]) | (near_gpu != ref["near"]))[0]
+        if len(bad):
+            first = bad[0]
+            assert margin[first] < TIE_M, (
+                f"episode {e}: index mismatch at step {first} (gpu ti {ti_gpu[first]} near {near_gpu[first]}, oracle "
+                f"ti {ref['ti'][first]} near {ref['near'][first]}) with decision margin {margin[first]:.3e} m -- not a tie")
+            worst["ties"] += 1
+            n = first + 1     # beyond a flipped tie the two runs are different episodes: compare up to it
+            tr = tr[:n]
+        else:
+            assert st[abi.S_STEPS] == ref["steps"], (e, st[abi.S_STEPS], ref["steps"])
+            assert st[abi.S_FLAGS] == ref["status"], (e, st[abi.S_FLAGS], ref["status"])
+            assert st[abi.S_TARGET_IND] == ref["target_ind"] and st[abi.S_NEAREST_IND] == ref["nearest_ind"]
+            assert st[abi.S_CONE_HITS] == ref["cone_hits"], (e, st[abi.S_CONE_HITS], ref["cone_hits"])
+            assert st[abi.S_LAPS] == ref["laps"]
+            m = res.metrics[e]
+            rm = ref["metrics"]
+            assert abs(m[abi.M_LAP_TIME] - rm["lap_time"]) < LAP_TOL
+            assert abs(m[abi.M_LAT_MEAN] - rm["lateral_mean"]) < e_ct_tol
+            assert abs(m[abi.M_HEAD_MEAN] - rm["heading_mean"]) < yaw_tol * 10
+            if n > 1:
+                assert abs(m[abi.M_LAT_STD] - rm["lateral_std"]) < e_ct_tol
+                assert abs(m[abi.M_HEAD_STD] - rm["heading_std"]) < yaw_tol * 10
+            assert abs(m[abi.M_MAX_ABS_LAT] - ref["max_abs_lateral"]) < e_ct_tol
+            np.testing.assert_allclose(m[abi.M_X:abi.M_V + 1], ref["state"][:4], atol=2 * pos_tol, rtol=1e-6)
+        dpos = np.hypot(tr[:, abi.T_X] - ref["traj"][:n, 0], tr[:, abi.T_Y] - ref["traj"][:n, 1]).max()
+        dyaw = np.abs(tr[:, abi.T_YAW] - ref["traj"][:n, 2]).max()
+        assert dpos < pos_tol, (e, dpos)
+        assert dyaw < yaw_tol, (e, dyaw)
+        assert np.abs(tr[:, abi.T_V] - ref["traj"][:n, 3]).max() < 1e-3
+        assert np.abs(tr[:, abi.T_STEER] - ref["steer"][:n]).max() < 5e-4
+        assert np.abs(tr[:, abi.T_E_CT] - ref["e_ct"][:n]).max() < e_ct_tol
+        worst["pos"], worst["yaw"] = max(worst["pos"], dpos), max(worst["yaw"], dyaw)
+    return res, worst
+
+
+@pytest.fixture(scope="module")
+def oval(cuda_device):
+    ta = bgr.tracks.stadium_oval(1024)
+    return ta, bgr.Track.from_arrays(ta, cone_reach=4.0)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_config1_single_trackdrive_episode(oval, precision):
+    """BASELINE config 1: one Trackdrive episode, pure pursuit + PID + kinematic bicycle on the oval,
+    2 000 steps over the 4-lap unrolled centreline (more than a full lap)."""
+    ta, track = oval
+    cfg = bgr.RolloutConfig(steer="pure_pursuit", accel="pid", model="kinematic", precision=precision,
+                            max_steps=2000, laps=4)
+    params = bgr.default_params(1)
+    init = bgr.initial_states(ta, 1)
+    res, worst = compare(ta, track, cfg, params, init, [0])
+    assert res.status[0, abi.S_STEPS] == 2000 and res.status[0, abi.S_FLAGS] == abi.ST_TIMEOUT
+    assert res.status[0, abi.S_LAPS] >= 2
+    if precision == "fp64":
+        assert worst["pos"] < 1e-6 and worst["yaw"] < 1e-7      # float32 parameter rows only
+
+
+@pytest.mark.parametrize("steer,accel,model", [
+    ("pure_pursuit", "pid", "kinematic"), ("pure_pursuit", "pid", "dynamic"), ("pure_pursuit", "lqg", "kinematic"),
+    ("pure_pursuit", "lqg", "dynamic"), ("stanley", "pid", "kinematic"), ("stanley", "pid", "dynamic"),
+    ("stanley", "lqg", "kinematic"), ("stanley", "lqg", "dynamic")])
+def test_every_law_model_combination_over_a_full_lap(oval, steer, accel, model):
+    """All 8 kernel specialisations, a batch with spread parameters, stop after one completed lap."""
+    ta, track = oval
+    E = 24
+    cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=2, laps_target=1)
+    params = bgr.default_params(E)
+    rng = np.random.default_rng(7)
+    params[:, abi.P_LF] = rng.uniform(3.0, 8.0, E)
+    params[:, abi.P_KP] = rng.uniform(0.2, 0.8, E)
+    params[:, abi.P_K_STANLEY] = rng.uniform(0.5, 2.0, E)
+    params[:, abi.P_K_SOFT] = rng.uniform(0.05, 1.0, E)
+    params[:, abi.P_MU] = rng.uniform(0.7, 1.2, E)
+    init = bgr.initial_states(ta, E, lateral_offset=rng.uniform(-0.5, 0.5, E), yaw_offset=rng.uniform(-0.1, 0.1, E))
+    res, worst = compare(ta, track, cfg, params, init, range(0, E, 3))
+    assert np.all(res.status[:, abi.S_FLAGS] & (abi.ST_LAPS_DONE | abi.ST_TIMEOUT))
+    assert np.count_nonzero(res.status[:, abi.S_FLAGS] & abi.ST_LAPS_DONE) >= E // 2
+    assert worst["ties"] <= 1
+
+
+def test_cone_hits_are_exact(oval):
+    """Cars started off the centreline clip cones: distinct-cone counts must equal the oracle's."""
+    ta, track = oval
+    E = 16
+    cfg = bgr.RolloutConfig(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=900, laps=2,
+                            hit_radius=0.6)
+    params = bgr.default_params(E)
+    params[:, abi.P_LF] = np.linspace(2.5, 9.0, E)
+    init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-1.4, 1.4, E))
+    res, _ = compare(ta, track, cfg, params, init, range(E), e_ct_tol=2e-3)
+    assert res.status[:, abi.S_CONE_HITS].max() > 0, "the test must actually hit cones"
+    assert res.aggregate[abi.A_CONE_HITS] == res.status[:, abi.S_CONE_HITS].sum()
+
+
+def test_config5_skidpad_monte_carlo_noise(cuda_device):
+    """Skidpad figure-eight (self-crossing path: the nearest search's exactness guard must fall back to the
+    global scan at the crossing) with Philox observation noise and perturbed cones, Stanley and pure pursuit."""
+    ta = bgr.tracks.skidpad(2048)
+    track = bgr.Track.from_arrays(ta, cone_reach=4.0)
+    noise = loop.NoiseSpec(seed=20261022, sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1, sigma_cone=0.05)
+    E = 8
+    for steer, accel, model in (("stanley", "lqg", "dynamic"), ("pure_pursuit", "pid", "kinematic"),
+                                ("stanley", "pid", "kinematic")):
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1200, laps=1, hit_radius=0.5,
+                                sigma_xy=noise.sigma_xy, sigma_yaw=noise.sigma_yaw, sigma_v=noise.sigma_v,
+                                sigma_cone=noise.sigma_cone, noise_seed=noise.seed, episode_id_base=1000)
+        params = bgr.sweeps.monte_carlo_params(E, start=1000)
+        init = bgr.initial_states(ta, E, index=0)
+        init[:, abi.YAW] = 0.0
+        # noise is drawn in the kernel's precision: fp32 Box-Muller vs the oracle's fp64 differ by ~1e-6 sigma,
+        # hence the slightly wider position budget for the noisy runs
+        res, worst = compare(ta, track, cfg, params, init, range(0, E, 2), noise=noise, pos_tol=2e-3, yaw_tol=2e-4,
+                             e_ct_tol=2e-3)
+        if steer == "stanley":
+            assert res.status[:, abi.S_FALLBACKS].min() > 0, "the crossing must trigger the exact global scan"
+
+
+def test_host_buffer_entry_point_equals_device_path(oval, cuda_device):
+    """bgr_rollout_host (numpy in / numpy out, copies inside) == bgr_rollout on device tensors, bit for bit."""
+    import torch
+    ta, track = oval
+    E = 1000                                     # not a multiple of the 256-thread CTA
+    cfg = bgr.RolloutConfig(steer="stanley", accel="lqg", model="dynamic", max_steps=300)
+    params = bgr.sweeps.stanley_lqg_params(E)
+    init = bgr.initial_states(ta, E)
+    host = bgr.rollout(track, cfg, params, init, aggregate=True)
+    dev = bgr.rollout(track, cfg, torch.from_numpy(params).to(cuda_device), torch.from_numpy(init).to(cuda_device),
+                      aggregate=True)
+    assert np.array_equal(host.metrics, dev.metrics.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(host.status, dev.status.cpu().numpy())
+    assert np.array_equal(host.aggregate, dev.aggregate.cpu().numpy())
+    assert host.aggregate[abi.A_EPISODES] == E and host.aggregate[abi.A_STEPS] == host.status[:, abi.S_STEPS].sum()
+
+
+def test_batched_equals_one_at_a_time_and_order_does_not_matter(oval):
+    """Episodes are independent: a batch == the same rows run one per call; permuting rows permutes results;
+    contiguous shards (with episode_id_base) concatenate to the whole -- all bit-identical."""
+    ta, track = oval
+    E = 600
+    cfg = bgr.RolloutConfig(steer="pure_pursuit", accel="pid", model="dynamic", max_steps=400, laps=2,
+                            sigma_xy=0.02, sigma_v=0.05, noise_seed=5)
+    params = bgr.sweeps.pp_sweep_params(E, start=12345)
+    init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.3, 0.3, E))
+    whole = bgr.rollout(track, cfg, params, init)
+    for e in (0, 255, 256, 599):
+        c1 = bgr.RolloutConfig(**{**cfg.__dict__, "episode_id_base": e})
+        one = bgr.rollout(track, c1, params[e:e + 1], init[e:e + 1])
+        assert np.array_equal(one.metrics[0], whole.metrics[e], equal_nan=True)
+        assert np.array_equal(one.status[0], whole.status[e])
+    # shards
+    parts_m, parts_s = [], []
+    for lo, hi in (bgr.sharding.shard_range(E, r, 3) for r in range(3)):
+        c = bgr.RolloutConfig(**{**cfg.__dict__, "episode_id_base": lo})
+        r = bgr.rollout(track, c, params[lo:hi], init[lo:hi])
+        parts_m.append(r.metrics)
+        parts_s.append(r.status)
+    assert np.array_equal(np.concatenate(parts_m), whole.metrics, equal_nan=True)
+    assert np.array_equal(np.concatenate(parts_s), whole.status)
+    # permutation (noise off: the noise stream is keyed by the episode id = row position)
+    cfg0 = bgr.RolloutConfig(steer="pure_pursuit", accel="pid", model="dynamic", max_steps=400, laps=2)
+    base = bgr.rollout(track, cfg0, params, init)
+    perm = np.random.default_rng(3).permutation(E)
+    shuf = bgr.rollout(track, cfg0, params[perm], init[perm])
+    assert np.array_equal(shuf.metrics, base.metrics[perm], equal_nan=True)
+    assert np.array_equal(shuf.status, base.status[perm])
+
+
+def test_lean_and_full_kernel_builds_agree(oval):
+    """The production (lean) build and the full build (audit channel on) are the same arithmetic."""
+    ta, track = oval
+    E = 512
+    for steer, accel, model in (("pure_pursuit", "pid", "kinematic"), ("stanley", "lqg", "dynamic")):
+        params = bgr.sweeps.pp_sweep_params(E, start=777)
+        init = bgr.initial_states(ta, E)
+        lean = bgr.rollout(track, bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=500, laps=2),
+                           params, init)
+        full = bgr.rollout(track, bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=500, laps=2,
+                                                    audit=True), params, init)
+        assert np.array_equal(lean.metrics, full.metrics, equal_nan=True)
+        cols = [abi.S_FLAGS, abi.S_STEPS, abi.S_TARGET_IND, abi.S_NEAREST_IND, abi.S_LAPS, abi.S_FALLBACKS]
+        assert np.array_equal(lean.status[:, cols], full.status[:, cols])
+
+
+def test_edge_cases(oval, cuda_device):
+    ta, track = oval
+    cfg = bgr.RolloutConfig(max_steps=1)
+    # empty batch
+    res = bgr.rollout(track, cfg, bgr.default_params(0), np.zeros((0, 6)), aggregate=True)
+    assert res.metrics.shape == (0, abi.N_METRICS) and res.aggregate[abi.A_EPISODES] == 0
+    # a single logged row: pandas std of one row is NaN, lap time 0
+    res = bgr.rollout(track, cfg, bgr.default_params(3), bgr.initial_states(ta, 3))
+    assert np.all(np.isnan(res.metrics[:, abi.M_LAT_STD])) and np.all(res.metrics[:, abi.M_LAP_TIME] == 0.0)
+    assert np.all(res.status[:, abi.S_STEPS] == 1)
+    # open path: pure pursuit ends when the target reaches the last index (old/animation_loop.py:71)
+    n = 200
+    line = bgr.Track(np.linspace(0, 40, n), np.zeros(n), None, closed=False)
+    ltr = bgr.tracks.TrackArrays(np.linspace(0, 40, n), np.zeros(n), np.zeros(n), False)
+    cfg = bgr.RolloutConfig(max_steps=3000, laps=1)
+    init = bgr.initial_states(ltr, 2, v0=3.0)
+    res, _ = compare(ltr, line, cfg, bgr.default_params(2), init, [0, 1])
+    assert np.all(res.status[:, abi.S_FLAGS] == abi.ST_PATH_END) and np.all(res.status[:, abi.S_TARGET_IND] == n - 1)
+    # non-finite state is flagged, not propagated silently
+    bad = bgr.initial_states(ta, 1)
+    bad[0, abi.V] = np.inf
+    res = bgr.rollout(track, bgr.RolloutConfig(max_steps=50), bgr.default_params(1), bad)
+    assert res.status[0, abi.S_FLAGS] & abi.ST_NONFINITE
+    # a centreline too long for the shared-memory staging budget is refused, not truncated
+    big = 20000
+    th = np.linspace(0, 2 * np.pi, big, endpoint=False)
+    with pytest.raises(abi.BgrError) as ei:
+        bgr.Track(500 * np.cos(th), 500 * np.sin(th), None, closed=True)
+    assert ei.value.code == abi.BGR_ERR_TOO_LARGE
+    # wrong shapes / dtypes are rejected on the host side
+    with pytest.raises(ValueError):
+        bgr.rollout(track, cfg, np.zeros((2, 8), np.float32), np.zeros((2, 6)))
+
+
+def test_full_size_properties_config2(oval, cuda_device):
+    """BASELINE config 2 at FULL size on the GPU (1 Mi episodes x 2 000 steps): properties that do not need the
+    oracle at that size -- every episode ran all 2 000 steps, aggregates are the fixed-order sum of the rows,
+    a strided sample of episodes re-run alone is bit-identical, and a handful are checked against the oracle."""
+    import torch
+    ta, track = oval
+    E = 1 << 20
+    cfg = bgr.RolloutConfig(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=2000, laps=8)
+    params = bgr.sweeps.pp_sweep_params(E)
+    init = bgr.initial_states(ta, E)
+    res = bgr.rollout(track, cfg, torch.from_numpy(params).to(cuda_device), torch.from_numpy(init).to(cuda_device),
+                      aggregate=True)
+    status = res.status.cpu().numpy()
+    metrics = res.metrics.cpu().numpy()
+    agg = res.aggregate.cpu().numpy()
+    assert np.all(status[:, abi.S_STEPS] == 2000) and np.all(status[:, abi.S_FLAGS] == abi.ST_TIMEOUT)
+    assert agg[abi.A_EPISODES] == E and agg[abi.A_STEPS] == 2000.0 * E
+    assert np.isclose(agg[abi.A_SUM_LAT_MEAN], metrics[:, abi.M_LAT_MEAN].astype(np.float64).sum(), rtol=1e-6)
+    assert np.all(np.isfinite(metrics))
+    sample = np.arange(0, E, E // 16) + 37
+    again = bgr.rollout(track, cfg, params[sample], init[sample])
+    assert np.array_equal(again.metrics, metrics[sample]) and np.array_equal(again.status, status[sample])
+    for e in sample[:3]:
+        spec = loop.RolloutSpec(max_steps=2000, laps=8)
+        ref = loop.rollout_episode(otrack(ta), spec, params[e].astype(np.float64), init[e], record=False)
+        if status[e, abi.S_TARGET_IND] == ref["target_ind"]:
+            assert abs(metrics[e, abi.M_LAT_MEAN] - ref["metrics"]["lateral_mean"]) < 1e-3
+            assert np.hypot(metrics[e, abi.M_X] - ref["state"][0], metrics[e, abi.M_Y] - ref["state"][1]) < 2e-3
