@@ -309,7 +309,7 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   DeviceInfo di;
   int rc = device_info(device, &di);
   if (rc != BGR_OK) return rc;
-  const int n_pad = (n + 3) & ~3;
+  const int n_pad = (n + 8 + 3) & ~3;   // cyclic pad of >= 8 entries past the lap end
   if (rollout_smem_bytes<float>(n_pad) > static_cast<size_t>(di.max_smem_optin)) {
     set_error("bgr_track_create: %d waypoints need %zu B of shared memory per CTA, device offers %d", n,
               rollout_smem_bytes<float>(n_pad), di.max_smem_optin);
@@ -369,7 +369,7 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   std::vector<D4> attr_d(n_pad);
   std::vector<float> guard2(n_pad);
   for (int j = 0; j < n_pad; ++j) {
-    const int s = std::min(j, n - 1);
+    const int s = j % n;   // cyclic pad
     const double sn = std::sin(t->path_yaw[s]), cs = std::cos(t->path_yaw[s]);
     xy_d[j] = make_double2(t->x[s], t->y[s]);
     attr_d[j] = D4{t->kappa[s], t->path_yaw[s], sn, cs};
@@ -595,6 +595,9 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   A.l_f = cfg->l_f;
   A.l_r = cfg->l_r;
   A.max_steer = cfg->max_steer;
+  A.inv_dt = 1.0 / cfg->dt;
+  A.inv_wheelbase = 1.0 / cfg->wheelbase;
+  A.tan_max_steer = std::tan(cfg->max_steer);
   A.max_accel = cfg->max_accel;
   A.max_decel = cfg->max_decel;
   A.hit_radius = cfg->hit_radius;

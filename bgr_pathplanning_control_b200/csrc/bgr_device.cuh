@@ -37,7 +37,8 @@ struct RT<double> {
   using R4 = D4;
 };
 
-// Device view of a track handle.  Per-waypoint tables (base lap, n_pad = n rounded up to 4):
+// Device view of a track handle.  Per-waypoint tables: the base lap followed by a cyclic pad (entry j >= n
+// replicates entry j - n) so that unrolled forward scans need no index wrap; n_pad = n + 8 rounded up to 4:
 //   xy    : (x, y)                                 nodes/planner.py:88
 //   attr  : (kappa, path_yaw, sin path_yaw, cos path_yaw)   nodes/planner.py:89, core/controllers.py:361-368
 //   guard2: squared exactness-guard radius of the local nearest search
@@ -76,6 +77,7 @@ struct RolloutArgs {
   double dt, wheelbase, l_f, l_r, max_steer, max_accel, max_decel;
   double hit_radius, tie_eps;
   double lqr_k0, lqr_k1;
+  double inv_dt, inv_wheelbase, tan_max_steer;  // host-computed loop invariants of the fp32 kernels
   double sigma_xy, sigma_yaw, sigma_v, sigma_cone;
   uint32_t seed;
   int32_t cones_on;
@@ -231,6 +233,49 @@ __device__ __forceinline__ void gaussians4(U4 r, Real z[4]) {
   sincos_r(Real(kTwoPi) * ud, &s, &c);
   z[2] = rc * c;
   z[3] = rc * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-CTA partial aggregates (fixed order: lane shuffle tree, then one thread per slot over the warps):
+// deterministic, no atomics.  Reuses the track's shared memory, hence the leading barrier.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_aggregate(const RolloutArgs& A, unsigned char* smem, bool active, int steps,
+                                                int flags, int cone_hits, double lat_mean, double lat_std,
+                                                double lap_time) {
+  if (A.block_partials == nullptr) return;
+  double vals[BGR_N_AGG];
+  const bool finished = active && (flags & (BGR_ST_PATH_END | BGR_ST_LAPS_DONE));
+  vals[BGR_A_EPISODES] = active ? 1.0 : 0.0;
+  vals[BGR_A_STEPS] = static_cast<double>(steps);
+  vals[BGR_A_SUM_LAT_MEAN] = active ? lat_mean : 0.0;
+  vals[BGR_A_SUM_LAT_STD] = (active && steps > 1) ? lat_std : 0.0;
+  vals[BGR_A_SUM_LAP_TIME] = active ? lap_time : 0.0;
+  vals[BGR_A_MIN_LAP_TIME] = finished ? lap_time : 1e300;
+  vals[BGR_A_CONE_HITS] = static_cast<double>(cone_hits);
+  vals[BGR_A_FINISHED] = finished ? 1.0 : 0.0;
+  __syncthreads();  // everyone is done with the track tables: reuse shared memory
+  double* red = reinterpret_cast<double*>(smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < BGR_N_AGG; ++a) {
+    double x = vals[a];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double o = __shfl_down_sync(0xffffffffu, x, off);
+      x = (a == BGR_A_MIN_LAP_TIME) ? fmin(x, o) : x + o;
+    }
+    if (lane == 0) red[warp * BGR_N_AGG + a] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < BGR_N_AGG) {
+    const int a = threadIdx.x;
+    double x = red[a];
+    for (int w = 1; w < kRolloutThreads / 32; ++w) {
+      const double o = red[w * BGR_N_AGG + a];
+      x = (a == BGR_A_MIN_LAP_TIME) ? fmin(x, o) : x + o;
+    }
+    A.block_partials[static_cast<size_t>(blockIdx.x) * BGR_N_AGG + a] = x;
+  }
 }
 
 constexpr uint32_t kStreamObs = 0;

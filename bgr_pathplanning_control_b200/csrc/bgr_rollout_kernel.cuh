@@ -1,4 +1,5 @@
-// The closed-loop rollout kernel: ONE EPISODE PER THREAD, the whole time loop in-kernel, vehicle /
+// The fp64 AUDIT closed-loop rollout kernel (reference operation order; the production fp32 kernel is
+// bgr_rollout_f32.cuh): ONE EPISODE PER THREAD, the whole time loop in-kernel, vehicle /
 // controller / metric state in registers, the base-lap track tables staged once per CTA into shared
 // memory by TMA bulk copies.  No tensor cores: nothing here is a dense contraction.
 //
@@ -535,41 +536,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
     }
   }
 
-  // ---- per-CTA partial aggregates (fixed order: lane tree, then warp 0 over warps) ----
-  if (A.block_partials != nullptr) {
-    double vals[BGR_N_AGG];
-    vals[BGR_A_EPISODES] = active ? 1.0 : 0.0;
-    vals[BGR_A_STEPS] = static_cast<double>(steps);
-    vals[BGR_A_SUM_LAT_MEAN] = active ? lat_mean : 0.0;
-    vals[BGR_A_SUM_LAT_STD] = (active && steps > 1) ? lat_std : 0.0;
-    vals[BGR_A_SUM_LAP_TIME] = active ? lap_time : 0.0;
-    vals[BGR_A_MIN_LAP_TIME] = (active && (flags & (BGR_ST_PATH_END | BGR_ST_LAPS_DONE))) ? lap_time : 1e300;
-    vals[BGR_A_CONE_HITS] = static_cast<double>(cone_hits);
-    vals[BGR_A_FINISHED] = (active && (flags & (BGR_ST_PATH_END | BGR_ST_LAPS_DONE))) ? 1.0 : 0.0;
-    __syncthreads();  // everyone is done with the track tables: reuse shared memory
-    double* red = reinterpret_cast<double*>(smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int a = 0; a < BGR_N_AGG; ++a) {
-      double x = vals[a];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double o = __shfl_down_sync(0xffffffffu, x, off);
-        x = (a == BGR_A_MIN_LAP_TIME) ? fmin(x, o) : x + o;
-      }
-      if (lane == 0) red[warp * BGR_N_AGG + a] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < BGR_N_AGG) {
-      const int a = threadIdx.x;
-      double x = red[a];
-      for (int w = 1; w < kRolloutThreads / 32; ++w) {
-        const double o = red[w * BGR_N_AGG + a];
-        x = (a == BGR_A_MIN_LAP_TIME) ? fmin(x, o) : x + o;
-      }
-      A.block_partials[static_cast<size_t>(blockIdx.x) * BGR_N_AGG + a] = x;
-    }
-  }
+  block_aggregate(A, smem, active, steps, flags, cone_hits, lat_mean, lat_std, lap_time);
 }
 
 // Host-side launcher, one explicit specialisation per (Real, STEER, ACCEL, MODEL, EXTRAS).
