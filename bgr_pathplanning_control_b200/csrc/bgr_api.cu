@@ -309,7 +309,7 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   DeviceInfo di;
   int rc = device_info(device, &di);
   if (rc != BGR_OK) return rc;
-  const int n_pad = (n + 8 + 3) & ~3;   // cyclic pad of >= 8 entries past the lap end
+  const int n_pad = (n + 12 + 3) & ~3;   // fp32 xy table: 4 cyclic entries in front, >= 8 behind (bgr_rollout_f32.cuh)
   if (rollout_smem_bytes<float>(n_pad) > static_cast<size_t>(di.max_smem_optin)) {
     set_error("bgr_track_create: %d waypoints need %zu B of shared memory per CTA, device offers %d", n,
               rollout_smem_bytes<float>(n_pad), di.max_smem_optin);
@@ -373,7 +373,8 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     const double sn = std::sin(t->path_yaw[s]), cs = std::cos(t->path_yaw[s]);
     xy_d[j] = make_double2(t->x[s], t->y[s]);
     attr_d[j] = D4{t->kappa[s], t->path_yaw[s], sn, cs};
-    xy_f[j] = make_float2(static_cast<float>(t->x[s]), static_cast<float>(t->y[s]));
+    const int sf = ((j - 4) % n + n) % n;   // fp32 xy table entry j holds waypoint j - 4 (front pad)
+    xy_f[j] = make_float2(static_cast<float>(t->x[sf]), static_cast<float>(t->y[sf]));
     attr_f[j] = make_float4(static_cast<float>(t->kappa[s]), static_cast<float>(t->path_yaw[s]),
                             static_cast<float>(sn), static_cast<float>(cs));
     // shrink by 1e-4 relative + 1e-4 m: the in-slab test itself runs in fp32 on rounded waypoints
@@ -598,10 +599,26 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   A.inv_dt = 1.0 / cfg->dt;
   A.inv_wheelbase = 1.0 / cfg->wheelbase;
   A.tan_max_steer = std::tan(cfg->max_steer);
+  A.f.dt = static_cast<float>(cfg->dt);
+  A.f.inv_dt = static_cast<float>(1.0 / cfg->dt);
+  A.f.WB = static_cast<float>(cfg->wheelbase);
+  A.f.inv_WB = static_cast<float>(1.0 / cfg->wheelbase);
+  A.f.l_f = static_cast<float>(cfg->l_f);
+  A.f.l_r = static_cast<float>(cfg->l_r);
+  A.f.max_steer = static_cast<float>(cfg->max_steer);
+  A.f.tan_max_steer = static_cast<float>(std::tan(cfg->max_steer));
+  A.f.max_accel = static_cast<float>(cfg->max_accel);
+  A.f.max_decel = static_cast<float>(cfg->max_decel);
+  A.f.hit_radius = static_cast<float>(cfg->hit_radius);
+  A.f.sigma_xy = static_cast<float>(cfg->sigma_xy);
+  A.f.sigma_yaw = static_cast<float>(cfg->sigma_yaw);
+  A.f.sigma_v = static_cast<float>(cfg->sigma_v);
+  A.f.sigma_cone = static_cast<float>(cfg->sigma_cone);
   A.max_accel = cfg->max_accel;
   A.max_decel = cfg->max_decel;
   A.hit_radius = cfg->hit_radius;
   A.tie_eps = cfg->tie_eps > 0.0 ? cfg->tie_eps : 2e-5;
+  A.f.tie_eps = static_cast<float>(A.tie_eps);
   A.sigma_xy = cfg->sigma_xy;
   A.sigma_yaw = cfg->sigma_yaw;
   A.sigma_v = cfg->sigma_v;
@@ -623,11 +640,14 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
 
   // LQG: LQR gain + the shared Kalman gain sequence
   double* d_kf = nullptr;
+  float2* d_kf_f = nullptr;
   if (cfg->accel_kind == BGR_ACCEL_LQG) {
     double K[2];
     lqr_gain_host(cfg->dt, K);
     A.lqr_k0 = K[0];
     A.lqr_k1 = K[1];
+    A.f.K0 = static_cast<float>(K[0]);
+    A.f.K1 = static_cast<float>(K[1]);
     int kf_len = cfg->max_steps;
     if (sp.ctrl_in != nullptr) kf_len = 4096;  // single-step API: index carried by the caller, clamped in-kernel
     std::vector<double> gains(static_cast<size_t>(kf_len) * 2);
@@ -636,6 +656,12 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
     BGR_CUDA(cudaMemcpyAsync(d_kf, gains.data(), gains.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     BGR_CUDA(cudaStreamSynchronize(stream));  // `gains` is pageable host memory that dies with this scope
     A.kf_gain = d_kf;
+    std::vector<float2> gains_f(static_cast<size_t>(kf_len));
+    for (int i = 0; i < kf_len; ++i) gains_f[i] = make_float2(static_cast<float>(gains[2 * i]), static_cast<float>(gains[2 * i + 1]));
+    BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_kf_f), gains_f.size() * sizeof(float2), stream));
+    BGR_CUDA(cudaMemcpyAsync(d_kf_f, gains_f.data(), gains_f.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
+    BGR_CUDA(cudaStreamSynchronize(stream));
+    A.kf_gain_f = d_kf_f;
     A.kf_len = kf_len;
   }
   double* d_partials = nullptr;
@@ -665,6 +691,7 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   }
   if (d_partials != nullptr) cudaFreeAsync(d_partials, stream);
   if (d_kf != nullptr) cudaFreeAsync(d_kf, stream);
+  if (d_kf_f != nullptr) cudaFreeAsync(d_kf_f, stream);
   return check_cuda(err, "rollout kernel launch");
 }
 

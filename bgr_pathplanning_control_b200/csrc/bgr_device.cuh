@@ -58,14 +58,23 @@ struct TrackView {
   float ds_max;
 };
 
+// float views of the configuration, converted once on the host (the fp32 kernels read them straight from the
+// constant bank instead of converting doubles inside the time loop)
+struct RolloutF32 {
+  float dt, inv_dt, WB, inv_WB, l_f, l_r, max_steer, tan_max_steer, max_accel, max_decel;
+  float tie_eps, hit_radius, K0, K1, sigma_xy, sigma_yaw, sigma_v, sigma_cone;
+};
+
 struct RolloutArgs {
   TrackView trk;
+  RolloutF32 f;
   const float* params;
   const double* init;
   float* metrics;
   int32_t* status;
   double* traj;
   const double* kf_gain;  // [kf_len][2] shared Kalman gain sequence (LQG) or nullptr
+  const float2* kf_gain_f; // the same sequence rounded to fp32 (production kernels)
   int32_t kf_len;
   double* block_partials; // [gridDim.x][BGR_N_AGG] or nullptr
   long long n_episodes;
