@@ -296,6 +296,7 @@ def run_b200(args):
     gather_ms = None
     if world > 1:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bgr.sharding.gather_results(out.metrics, out.status, out.aggregate, E * world)   # warm-up: NCCL channels
         barrier()
         g0.record()
         m_all, s_all, agg_all = bgr.sharding.gather_results(out.metrics, out.status, out.aggregate, E * world)

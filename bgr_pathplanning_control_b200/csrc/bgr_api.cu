@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -270,6 +271,10 @@ extern "C" void bgr_track_destroy(bgr_track_t* t) {
   cudaFree(t->cone_range);
   cudaFree(t->cone_list);
   cudaFree(t->cones);
+  for (auto& k : t->kf_tables) {
+    cudaFree(k.d_gain);
+    cudaFree(k.d_gain_f);
+  }
   cudaSetDevice(prev);
   delete t;
 }
@@ -526,41 +531,18 @@ int validate_cfg(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const c
   return BGR_OK;
 }
 
-int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes, const float* d_params,
-                 const double* d_init, float* d_metrics, int32_t* d_status, double* d_traj, double* d_aggregate,
-                 const StepPlumbing& sp, cudaStream_t stream) {
+struct Plan {
+  RolloutArgs A;
+  LaunchFn fn = nullptr;
+  size_t smem = 0;
+};
+
+// Validate the configuration, fill the kernel arguments that do not depend on the episode range, pick the kernel
+// specialisation and make sure the LQG tables are resident (cached on the track handle).
+int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const StepPlumbing& sp, bool want_traj,
+              cudaStream_t stream, Plan* plan) {
   int rc = validate_cfg(track, cfg, "bgr_rollout");
   if (rc != BGR_OK) return rc;
-  if (n_episodes < 0 || n_episodes > (1LL << 31) * kRolloutThreads) {
-    set_error("bgr_rollout: n_episodes %lld out of range", static_cast<long long>(n_episodes));
-    return BGR_ERR_BAD_ARG;
-  }
-  if (n_episodes == 0) {
-    if (d_aggregate != nullptr) {
-      double zero[BGR_N_AGG] = {0, 0, 0, 0, 0, 1e300, 0, 0};
-      BGR_CUDA(cudaMemcpyAsync(d_aggregate, zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
-      BGR_CUDA(cudaStreamSynchronize(stream));
-    }
-    return BGR_OK;
-  }
-  if ((d_params == nullptr && sp.params64 == nullptr) || d_init == nullptr || d_metrics == nullptr ||
-      d_status == nullptr) {
-    set_error("bgr_rollout: d_params / d_init_state / d_metrics / d_status is NULL");
-    return BGR_ERR_BAD_ARG;
-  }
-  if ((reinterpret_cast<uintptr_t>(d_params) & 15) || (reinterpret_cast<uintptr_t>(d_metrics) & 15) ||
-      (reinterpret_cast<uintptr_t>(d_init) & 7)) {
-    set_error("bgr_rollout: d_params and d_metrics must be 16-byte aligned, d_init_state 8-byte aligned");
-    return BGR_ERR_BAD_ARG;
-  }
-
-  int prev = 0;
-  cudaGetDevice(&prev);
-  struct Restore {
-    int dev;
-    ~Restore() { cudaSetDevice(dev); }
-  } restore{prev};
-  BGR_CUDA(cudaSetDevice(track->device));
   DeviceInfo di;
   rc = device_info(track->device, &di);
   if (rc != BGR_OK) return rc;
@@ -568,24 +550,18 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   const bool f64 = cfg->precision == BGR_PRECISION_FP64;
   const bool cones_on = cfg->hit_radius > 0.0 && track->n_cones > 0;
   const bool noise_on = cfg->sigma_xy > 0.0 || cfg->sigma_yaw > 0.0 || cfg->sigma_v > 0.0;
-  const bool full = f64 || cones_on || noise_on || d_traj != nullptr || (cfg->flags & BGR_CFG_AUDIT) || sp.force_full;
+  const bool full = f64 || cones_on || noise_on || want_traj || (cfg->flags & BGR_CFG_AUDIT) || sp.force_full;
 
-  const size_t smem = f64 ? rollout_smem_bytes<double>(track->n_pad) : rollout_smem_bytes<float>(track->n_pad);
-  if (smem > static_cast<size_t>(di.max_smem_optin)) {
-    set_error("bgr_rollout: track needs %zu B of shared memory per CTA in this precision, device offers %d", smem,
-              di.max_smem_optin);
+  plan->smem = f64 ? rollout_smem_bytes<double>(track->n_pad) : rollout_smem_bytes<float>(track->n_pad);
+  if (plan->smem > static_cast<size_t>(di.max_smem_optin)) {
+    set_error("bgr_rollout: track needs %zu B of shared memory per CTA in this precision, device offers %d",
+              plan->smem, di.max_smem_optin);
     return BGR_ERR_TOO_LARGE;
   }
 
-  RolloutArgs A;
+  RolloutArgs& A = plan->A;
   std::memset(&A, 0, sizeof(A));
   A.trk = track->view();
-  A.params = d_params;
-  A.init = d_init;
-  A.metrics = d_metrics;
-  A.status = d_status;
-  A.traj = d_traj;
-  A.n_episodes = n_episodes;
   A.episode_id_base = cfg->episode_id_base;
   A.max_steps = cfg->max_steps;
   A.laps = cfg->laps;
@@ -599,6 +575,14 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   A.inv_dt = 1.0 / cfg->dt;
   A.inv_wheelbase = 1.0 / cfg->wheelbase;
   A.tan_max_steer = std::tan(cfg->max_steer);
+  A.max_accel = cfg->max_accel;
+  A.max_decel = cfg->max_decel;
+  A.hit_radius = cfg->hit_radius;
+  A.tie_eps = cfg->tie_eps > 0.0 ? cfg->tie_eps : 2e-5;
+  A.sigma_xy = cfg->sigma_xy;
+  A.sigma_yaw = cfg->sigma_yaw;
+  A.sigma_v = cfg->sigma_v;
+  A.sigma_cone = cfg->sigma_cone;
   A.f.dt = static_cast<float>(cfg->dt);
   A.f.inv_dt = static_cast<float>(1.0 / cfg->dt);
   A.f.WB = static_cast<float>(cfg->wheelbase);
@@ -610,19 +594,11 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   A.f.max_accel = static_cast<float>(cfg->max_accel);
   A.f.max_decel = static_cast<float>(cfg->max_decel);
   A.f.hit_radius = static_cast<float>(cfg->hit_radius);
+  A.f.tie_eps = static_cast<float>(A.tie_eps);
   A.f.sigma_xy = static_cast<float>(cfg->sigma_xy);
   A.f.sigma_yaw = static_cast<float>(cfg->sigma_yaw);
   A.f.sigma_v = static_cast<float>(cfg->sigma_v);
   A.f.sigma_cone = static_cast<float>(cfg->sigma_cone);
-  A.max_accel = cfg->max_accel;
-  A.max_decel = cfg->max_decel;
-  A.hit_radius = cfg->hit_radius;
-  A.tie_eps = cfg->tie_eps > 0.0 ? cfg->tie_eps : 2e-5;
-  A.f.tie_eps = static_cast<float>(A.tie_eps);
-  A.sigma_xy = cfg->sigma_xy;
-  A.sigma_yaw = cfg->sigma_yaw;
-  A.sigma_v = cfg->sigma_v;
-  A.sigma_cone = cfg->sigma_cone;
   A.seed = cfg->noise_seed;
   A.cones_on = cones_on ? 1 : 0;
   A.noise_on = noise_on ? 1 : 0;
@@ -636,11 +612,8 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   A.params64 = sp.params64;
   A.step_out = sp.step_out;
 
-  const int grid = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
-
-  // LQG: LQR gain + the shared Kalman gain sequence
-  double* d_kf = nullptr;
-  float2* d_kf_f = nullptr;
+  // LQG: LQR gain + the shared, data-independent Kalman gain sequence (uploaded once per (dt, length) and kept
+  // on the track handle until it is destroyed)
   if (cfg->accel_kind == BGR_ACCEL_LQG) {
     double K[2];
     lqr_gain_host(cfg->dt, K);
@@ -650,49 +623,128 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
     A.f.K1 = static_cast<float>(K[1]);
     int kf_len = cfg->max_steps;
     if (sp.ctrl_in != nullptr) kf_len = 4096;  // single-step API: index carried by the caller, clamped in-kernel
-    std::vector<double> gains(static_cast<size_t>(kf_len) * 2);
-    kalman_gains_host(cfg->dt, kf_len, gains.data());
-    BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_kf), gains.size() * sizeof(double), stream));
-    BGR_CUDA(cudaMemcpyAsync(d_kf, gains.data(), gains.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
-    BGR_CUDA(cudaStreamSynchronize(stream));  // `gains` is pageable host memory that dies with this scope
-    A.kf_gain = d_kf;
-    std::vector<float2> gains_f(static_cast<size_t>(kf_len));
-    for (int i = 0; i < kf_len; ++i) gains_f[i] = make_float2(static_cast<float>(gains[2 * i]), static_cast<float>(gains[2 * i + 1]));
-    BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_kf_f), gains_f.size() * sizeof(float2), stream));
-    BGR_CUDA(cudaMemcpyAsync(d_kf_f, gains_f.data(), gains_f.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
-    BGR_CUDA(cudaStreamSynchronize(stream));
-    A.kf_gain_f = d_kf_f;
-    A.kf_len = kf_len;
+    std::lock_guard<std::mutex> lock(track->kf_mu);
+    const bgr_track::KfTable* hit = nullptr;
+    for (const auto& t : track->kf_tables)
+      if (t.dt == cfg->dt && t.len >= kf_len) hit = &t;
+    if (hit == nullptr) {
+      const int len = std::max(kf_len, 4096);
+      std::vector<double> gains(static_cast<size_t>(len) * 2);
+      kalman_gains_host(cfg->dt, len, gains.data());
+      std::vector<float2> gains_f(static_cast<size_t>(len));
+      for (int i = 0; i < len; ++i)
+        gains_f[i] = make_float2(static_cast<float>(gains[2 * i]), static_cast<float>(gains[2 * i + 1]));
+      bgr_track::KfTable t;
+      t.dt = cfg->dt;
+      t.len = len;
+      BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.d_gain), gains.size() * sizeof(double)));
+      BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.d_gain_f), gains_f.size() * sizeof(float2)));
+      BGR_CUDA(cudaMemcpy(t.d_gain, gains.data(), gains.size() * sizeof(double), cudaMemcpyHostToDevice));
+      BGR_CUDA(cudaMemcpy(t.d_gain_f, gains_f.data(), gains_f.size() * sizeof(float2), cudaMemcpyHostToDevice));
+      track->kf_tables.push_back(t);
+      hit = &track->kf_tables.back();
+    }
+    A.kf_gain = hit->d_gain;
+    A.kf_gain_f = hit->d_gain_f;
+    A.kf_len = hit->len;
   }
-  double* d_partials = nullptr;
+
+  if (f64) plan->fn = pick<double, true>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
+  else if (full) plan->fn = pick<float, true>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
+  else plan->fn = pick<float, false>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
+  (void)stream;
+  return BGR_OK;
+}
+
+// Launch the step kernel for `count` episodes whose rows start at the given pointers; `id_offset` is their global
+// position within the call (noise streams are keyed by the global episode id).  `d_partials` points at this
+// range's slice of the per-CTA aggregate partials (ranges start on CTA boundaries, so a chunked call produces the
+// same partials, in the same order, as a single launch).
+int launch_range(const Plan& plan, long long id_offset, long long count, const float* d_params, const double* d_init,
+                 float* d_metrics, int32_t* d_status, double* d_traj, double* d_partials, cudaStream_t stream) {
+  RolloutArgs A = plan.A;
+  A.params = d_params;
+  A.init = d_init;
+  A.metrics = d_metrics;
+  A.status = d_status;
+  A.traj = d_traj;
+  A.block_partials = d_partials;
+  A.n_episodes = count;
+  A.episode_id_base += id_offset;
+  const int grid = static_cast<int>((count + kRolloutThreads - 1) / kRolloutThreads);
+  cudaError_t err = plan.fn(A, grid, plan.smem, stream);
+  if (err == cudaSuccess) count_launch();
+  return check_cuda(err, "rollout kernel launch");
+}
+
+int check_rollout_buffers(int64_t n_episodes, const void* d_params, const void* d_params64, const void* d_init,
+                          const void* d_metrics, const void* d_status) {
+  if (n_episodes < 0 || n_episodes > (1LL << 31) * kRolloutThreads) {
+    set_error("bgr_rollout: n_episodes %lld out of range", static_cast<long long>(n_episodes));
+    return BGR_ERR_BAD_ARG;
+  }
+  if (n_episodes == 0) return BGR_OK;
+  if ((d_params == nullptr && d_params64 == nullptr) || d_init == nullptr || d_metrics == nullptr ||
+      d_status == nullptr) {
+    set_error("bgr_rollout: d_params / d_init_state / d_metrics / d_status is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(d_params) & 15) || (reinterpret_cast<uintptr_t>(d_metrics) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_init) & 7)) {
+    set_error("bgr_rollout: d_params and d_metrics must be 16-byte aligned, d_init_state 8-byte aligned");
+    return BGR_ERR_BAD_ARG;
+  }
+  return BGR_OK;
+}
+
+int empty_aggregate(double* d_aggregate, cudaStream_t stream) {
   if (d_aggregate != nullptr) {
+    const double zero[BGR_N_AGG] = {0, 0, 0, 0, 0, 1e300, 0, 0};
+    BGR_CUDA(cudaMemcpyAsync(d_aggregate, zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+    BGR_CUDA(cudaStreamSynchronize(stream));
+  }
+  return BGR_OK;
+}
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes, const float* d_params,
+                 const double* d_init, float* d_metrics, int32_t* d_status, double* d_traj, double* d_aggregate,
+                 const StepPlumbing& sp, cudaStream_t stream) {
+  int rc = validate_cfg(track, cfg, "bgr_rollout");
+  if (rc != BGR_OK) return rc;
+  rc = check_rollout_buffers(n_episodes, d_params, sp.params64, d_init, d_metrics, d_status);
+  if (rc != BGR_OK) return rc;
+  DeviceGuard guard(track->device);
+  if (n_episodes == 0) return empty_aggregate(d_aggregate, stream);
+  Plan plan;
+  rc = make_plan(track, cfg, sp, d_traj != nullptr, stream, &plan);
+  if (rc != BGR_OK) return rc;
+  const int grid = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
+  double* d_partials = nullptr;
+  if (d_aggregate != nullptr)
     BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_partials), static_cast<size_t>(grid) * BGR_N_AGG * sizeof(double),
                              stream));
-    A.block_partials = d_partials;
-  }
-
-  LaunchFn fn;
-  if (f64) fn = pick<double, true>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
-  else if (full) fn = pick<float, true>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
-  else fn = pick<float, false>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
-
   rc = ensure_events(track->device);
-  if (rc != BGR_OK) return rc;
-  BGR_CUDA(cudaEventRecord(g_last.start, stream));
-  cudaError_t err = fn(A, grid, smem, stream);
-  if (err == cudaSuccess) {
-    count_launch();
-    BGR_CUDA(cudaEventRecord(g_last.stop, stream));
-    g_last.valid = true;
-    if (d_partials != nullptr) {
-      err = launch_reduce_partials(d_partials, grid, d_aggregate, stream);
-      if (err == cudaSuccess) count_launch();
-    }
+  if (rc == BGR_OK) rc = check_cuda(cudaEventRecord(g_last.start, stream), "cudaEventRecord");
+  if (rc == BGR_OK) rc = launch_range(plan, 0, n_episodes, d_params, d_init, d_metrics, d_status, d_traj, d_partials, stream);
+  if (rc == BGR_OK) {
+    rc = check_cuda(cudaEventRecord(g_last.stop, stream), "cudaEventRecord");
+    g_last.valid = rc == BGR_OK;
+  }
+  if (rc == BGR_OK && d_partials != nullptr) {
+    rc = check_cuda(launch_reduce_partials(d_partials, grid, d_aggregate, stream), "aggregate reduction launch");
+    if (rc == BGR_OK) count_launch();
   }
   if (d_partials != nullptr) cudaFreeAsync(d_partials, stream);
-  if (d_kf != nullptr) cudaFreeAsync(d_kf, stream);
-  if (d_kf_f != nullptr) cudaFreeAsync(d_kf_f, stream);
-  return check_cuda(err, "rollout kernel launch");
+  return rc;
 }
 
 }  // namespace
@@ -745,6 +797,52 @@ struct DeviceScope {
 
 }  // namespace
 
+namespace {
+
+// Two internal streams + events per host thread and device: bgr_rollout_host pipelines the H2D copy of chunk c + 1
+// and the D2H copy of chunk c - 1 under the kernel of chunk c.
+struct Pipeline {
+  int device = -1;
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaEvent_t ready = nullptr;
+};
+thread_local Pipeline g_pipe;
+
+int ensure_pipeline(int device) {
+  if (g_pipe.device == device) return BGR_OK;
+  if (g_pipe.device >= 0) {
+    for (int i = 0; i < 2; ++i) {
+      cudaStreamDestroy(g_pipe.s[i]);
+      cudaEventDestroy(g_pipe.done[i]);
+    }
+    cudaEventDestroy(g_pipe.ready);
+    g_pipe.device = -1;
+  }
+  for (int i = 0; i < 2; ++i) {
+    BGR_CUDA(cudaStreamCreateWithFlags(&g_pipe.s[i], cudaStreamNonBlocking));
+    BGR_CUDA(cudaEventCreateWithFlags(&g_pipe.done[i], cudaEventDisableTiming));
+  }
+  BGR_CUDA(cudaEventCreateWithFlags(&g_pipe.ready, cudaEventDisableTiming));
+  g_pipe.device = device;
+  return BGR_OK;
+}
+
+// episodes per pipelined chunk (a multiple of the CTA size; BGR_HOST_CHUNK overrides it for tuning)
+long long host_chunk() {
+  static const long long v = [] {
+    long long c = 1 << 17;
+    if (const char* e = std::getenv("BGR_HOST_CHUNK")) {
+      const long long x = std::atoll(e);
+      if (x >= kRolloutThreads) c = x / kRolloutThreads * kRolloutThreads;
+    }
+    return c;
+  }();
+  return v;
+}
+
+}  // namespace
+
 extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
                                 const float* h_params, const double* h_init_state, float* h_metrics,
                                 int32_t* h_status, double* h_traj, double* h_aggregate, void* stream_) {
@@ -767,30 +865,75 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
   int32_t* d_status;
   double* d_traj = nullptr;
   double* d_agg = nullptr;
+  double* d_partials = nullptr;
   BGR_TRY(sc.get(&d_params, E * BGR_N_PARAMS));
   BGR_TRY(sc.get(&d_init, E * BGR_N_STATE));
   BGR_TRY(sc.get(&d_metrics, E * BGR_N_METRICS));
   BGR_TRY(sc.get(&d_status, E * BGR_N_STATUS));
-  const size_t traj_count = E * static_cast<size_t>(cfg->max_steps) * BGR_N_TRAJ;
+  const size_t S = static_cast<size_t>(cfg->max_steps);
   if (h_traj != nullptr) {
-    BGR_TRY(sc.get(&d_traj, traj_count));
-    BGR_CUDA(cudaMemsetAsync(d_traj, 0, traj_count * sizeof(double), stream));
+    BGR_TRY(sc.get(&d_traj, E * S * BGR_N_TRAJ));
+    BGR_CUDA(cudaMemsetAsync(d_traj, 0, E * S * BGR_N_TRAJ * sizeof(double), stream));
   }
-  if (h_aggregate != nullptr) BGR_TRY(sc.get(&d_agg, BGR_N_AGG));
-  if (E > 0) {
-    BGR_CUDA(cudaMemcpyAsync(d_params, h_params, E * BGR_N_PARAMS * sizeof(float), cudaMemcpyHostToDevice, stream));
-    BGR_CUDA(cudaMemcpyAsync(d_init, h_init_state, E * BGR_N_STATE * sizeof(double), cudaMemcpyHostToDevice, stream));
+  if (E == 0) {
+    if (h_aggregate != nullptr) {
+      const double zero[BGR_N_AGG] = {0, 0, 0, 0, 0, 1e300, 0, 0};
+      std::memcpy(h_aggregate, zero, sizeof(zero));
+    }
+    return BGR_OK;
+  }
+  const int grid_total = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
+  if (h_aggregate != nullptr) {
+    BGR_TRY(sc.get(&d_agg, BGR_N_AGG));
+    BGR_TRY(sc.get(&d_partials, static_cast<size_t>(grid_total) * BGR_N_AGG));
   }
   StepPlumbing sp;
-  BGR_TRY(rollout_impl(track, cfg, n_episodes, d_params, d_init, d_metrics, d_status, d_traj, d_agg, sp, stream));
-  if (E > 0) {
-    BGR_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, E * BGR_N_METRICS * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    BGR_CUDA(cudaMemcpyAsync(h_status, d_status, E * BGR_N_STATUS * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  Plan plan;
+  BGR_TRY(make_plan(track, cfg, sp, h_traj != nullptr, stream, &plan));
+  BGR_TRY(ensure_pipeline(track->device));
+  BGR_TRY(ensure_events(track->device));
+
+  // everything queued on the caller's stream so far (scratch allocation, memset) happens before the chunks
+  BGR_CUDA(cudaEventRecord(g_pipe.ready, stream));
+  BGR_CUDA(cudaStreamWaitEvent(g_pipe.s[0], g_pipe.ready, 0));
+  BGR_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ready, 0));
+  int c = 0;
+  const long long chunk = host_chunk();
+  for (long long e0 = 0; e0 < n_episodes; e0 += chunk, ++c) {
+    const long long cnt = std::min<long long>(chunk, n_episodes - e0);
+    const size_t n = static_cast<size_t>(cnt), o = static_cast<size_t>(e0);
+    cudaStream_t st = g_pipe.s[c & 1];
+    BGR_CUDA(cudaMemcpyAsync(d_params + o * BGR_N_PARAMS, h_params + o * BGR_N_PARAMS, n * BGR_N_PARAMS * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+    BGR_CUDA(cudaMemcpyAsync(d_init + o * BGR_N_STATE, h_init_state + o * BGR_N_STATE, n * BGR_N_STATE * sizeof(double),
+                             cudaMemcpyHostToDevice, st));
+    const bool last = e0 + cnt >= n_episodes;
+    if (last) BGR_CUDA(cudaEventRecord(g_last.start, st));
+    BGR_TRY(launch_range(plan, e0, cnt, d_params + o * BGR_N_PARAMS, d_init + o * BGR_N_STATE,
+                         d_metrics + o * BGR_N_METRICS, d_status + o * BGR_N_STATUS,
+                         d_traj != nullptr ? d_traj + o * S * BGR_N_TRAJ : nullptr,
+                         d_partials != nullptr ? d_partials + (o / kRolloutThreads) * BGR_N_AGG : nullptr, st));
+    if (last) {
+      BGR_CUDA(cudaEventRecord(g_last.stop, st));
+      g_last.valid = true;
+    }
+    BGR_CUDA(cudaMemcpyAsync(h_metrics + o * BGR_N_METRICS, d_metrics + o * BGR_N_METRICS,
+                             n * BGR_N_METRICS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BGR_CUDA(cudaMemcpyAsync(h_status + o * BGR_N_STATUS, d_status + o * BGR_N_STATUS, n * BGR_N_STATUS * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, st));
     if (h_traj != nullptr)
-      BGR_CUDA(cudaMemcpyAsync(h_traj, d_traj, traj_count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      BGR_CUDA(cudaMemcpyAsync(h_traj + o * S * BGR_N_TRAJ, d_traj + o * S * BGR_N_TRAJ,
+                               n * S * BGR_N_TRAJ * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
-  if (h_aggregate != nullptr)
+  for (int i = 0; i < 2; ++i) {
+    BGR_CUDA(cudaEventRecord(g_pipe.done[i], g_pipe.s[i]));
+    BGR_CUDA(cudaStreamWaitEvent(stream, g_pipe.done[i], 0));
+  }
+  if (h_aggregate != nullptr) {
+    BGR_CUDA(launch_reduce_partials(d_partials, grid_total, d_agg, stream));
+    count_launch();
     BGR_CUDA(cudaMemcpyAsync(h_aggregate, d_agg, BGR_N_AGG * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  }
   BGR_CUDA(cudaStreamSynchronize(stream));
   return BGR_OK;
 }

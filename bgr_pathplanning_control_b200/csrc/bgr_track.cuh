@@ -1,6 +1,7 @@
 // Host-side track handle: derived per-waypoint tables + device residency.
 #pragma once
 
+#include <mutex>
 #include <vector>
 
 #include "bgr_device.cuh"
@@ -18,6 +19,15 @@ struct bgr_track {
   int32_t* cone_range = nullptr;
   int32_t* cone_list = nullptr;
   double2* cones = nullptr;
+  // LQG Kalman gain sequences, uploaded on first use per (dt, length); freed with the handle
+  struct KfTable {
+    double dt = 0;
+    int len = 0;
+    double* d_gain = nullptr;
+    float2* d_gain_f = nullptr;
+  };
+  mutable std::mutex kf_mu;
+  mutable std::vector<KfTable> kf_tables;
   // host copies
   std::vector<double> x, y, kappa, path_yaw, guard_radius;
   double ds_min = 0, ds_max = 0, guard_min = 0, guard_median = 0;
