@@ -68,7 +68,7 @@ def _cpu_worker(job):
     track = loop.Track(ta.x, ta.y, ta.kappa, True, ta.cones)
     params = (bgr.sweeps.pp_sweep_params(count, start) if workload == "pp_sweep"
               else bgr.sweeps.stanley_lqg_params(count, start=start))
-    init = bgr.initial_states(ta, count)
+    init = bgr.initial_states(ta, count, v0=5.0 if model == "dynamic" else 0.0)
     spec = loop.RolloutSpec(steer=steer, accel=accel, model=model, max_steps=sim_steps, laps=laps)
     done = 0
     t0 = time.perf_counter()
@@ -248,7 +248,8 @@ def run_b200(args):
     make = bgr.sweeps.pp_sweep_params if args.workload == "pp_sweep" else \
         (lambda n, start: bgr.sweeps.stanley_lqg_params(n, start=start))
     h_params = [torch.from_numpy(make(E, (rank * n_sets + s) * 65537)).pin_memory() for s in range(n_sets)]
-    h_init = [torch.from_numpy(bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.2, 0.2, E) * (s % 2)))
+    v0 = 5.0 if model == "dynamic" else 0.0     # the Euler-integrated tyre model is unstable below ~3.2 m/s
+    h_init = [torch.from_numpy(bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.2, 0.2, E) * (s % 2), v0=v0))
               .pin_memory() for s in range(n_sets)]
     d_params = [t.to(dev) for t in h_params]
     d_init = [t.to(dev) for t in h_init]

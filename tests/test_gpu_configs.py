@@ -33,7 +33,7 @@ def test_config3_stanley_lqg_dynamic_4M_episodes_sharded(cuda_device):
         assert (lo, hi) == (g * per, (g + 1) * per)
         cfg = bgr.RolloutConfig(steer="stanley", accel="lqg", model="dynamic", max_steps=S, episode_id_base=lo)
         params = bgr.sweeps.stanley_lqg_params(hi - lo, start=lo)
-        init = bgr.initial_states(ta, hi - lo)
+        init = bgr.initial_states(ta, hi - lo, v0=5.0)   # above the Euler stability limit of the tyre model
         res = bgr.rollout(track, cfg, _dev(params, cuda_device), _dev(init, cuda_device), aggregate=True)
         metrics.append(res.metrics.cpu().numpy())
         status.append(res.status.cpu().numpy())
@@ -47,13 +47,14 @@ def test_config3_stanley_lqg_dynamic_4M_episodes_sharded(cuda_device):
     finite = ~(s[:, abi.S_FLAGS] & abi.ST_NONFINITE).astype(bool)
     assert finite.mean() > 0.999
     assert np.all(np.isfinite(m[finite]))
-    # most of the sweep (k, k_soft, mu, stiffness spread) tracks the oval within the cone line
+    # about half of the sweep (k, k_soft, mu, stiffness spread at up to 8.5 m/s) stays inside the cone line -- the
+    # oracle twin gives the same fraction (scripts/diag_parity.py); the rest is Stanley overshooting the R = 15 m bends
     on_track = m[:, abi.M_MAX_ABS_LAT] < 1.5
-    assert on_track.mean() > 0.5, on_track.mean()
+    assert 0.3 < on_track.mean() < 0.7, on_track.mean()
     # a window that straddles a shard boundary, run alone, reproduces the sharded rows bit for bit
     lo = per - 300
     cfg = bgr.RolloutConfig(steer="stanley", accel="lqg", model="dynamic", max_steps=S, episode_id_base=lo)
-    again = bgr.rollout(track, cfg, bgr.sweeps.stanley_lqg_params(600, start=lo), bgr.initial_states(ta, 600))
+    again = bgr.rollout(track, cfg, bgr.sweeps.stanley_lqg_params(600, start=lo), bgr.initial_states(ta, 600, v0=5.0))
     assert np.array_equal(again.metrics, m[lo:lo + 600], equal_nan=True)
     assert np.array_equal(again.status, s[lo:lo + 600])
     # oracle spot check on sampled on-track episodes
@@ -62,7 +63,7 @@ def test_config3_stanley_lqg_dynamic_4M_episodes_sharded(cuda_device):
     for e in np.nonzero(on_track)[0][:: max(1, on_track.sum() // 4)][:4]:
         p = bgr.sweeps.stanley_lqg_params(1, start=int(e))[0].astype(np.float64)
         ref = loop.rollout_episode(otrack, loop.RolloutSpec(steer="stanley", accel="lqg", model="dynamic", max_steps=S),
-                                   p, bgr.initial_states(ta, 1)[0], record=False)
+                                   p, bgr.initial_states(ta, 1, v0=5.0)[0], record=False)
         assert s[e, abi.S_STEPS] == ref["steps"] and s[e, abi.S_LAPS] == ref["laps"]
         assert abs(m[e, abi.M_LAT_MEAN] - ref["metrics"]["lateral_mean"]) < 1e-3
         assert abs(m[e, abi.M_LAT_STD] - ref["metrics"]["lateral_std"]) < 1e-3

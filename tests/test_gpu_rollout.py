@@ -309,34 +309,55 @@ def test_full_size_properties_config2(oval, cuda_device):
                                                     ("pure_pursuit", "lqg", "dynamic", 8), ("stanley", "pid", "kinematic", 1)])
 def test_parity_at_scale_against_the_c_twin(oval, steer, accel, model, laps):
     """768 full-length episodes (2 000 steps, ~2.9 laps) of the bench sweeps, fp32 production kernel (audit build)
-    vs the plain-C fp64 oracle twin (oracle/c, pinned to the numpy oracle).  The kernel's near-tie audit channel
-    must account for EVERY index mismatch: an episode with no flagged decision has to reproduce the oracle's final
-    target / nearest index, lap count and step count exactly and its final pose within the north-star tolerance."""
+    vs the plain-C fp64 oracle twin (oracle/c, pinned to the numpy oracle).
+
+    * The kernel's near-tie audit channel must account for EVERY index mismatch: an on-track episode with no flagged
+      decision reproduces the oracle's flags, step count, final target / nearest index and lap count exactly.
+    * Every WELL-CONDITIONED episode ends within the north-star tolerances (1e-3 m, 1e-4 rad, 1e-3 s).  Conditioning
+      is measured on the oracle itself: the fp64 twin is re-run from an initial position moved by 1e-7 m (one fp32
+      ulp of a coordinate); episodes whose fp64 end pose moves by more than 1e-5 m under that nudge amplify ANY
+      rounding by > 100x over the run (oscillating Stanley / tyre-model sweeps do) and cannot be matched by any
+      finite-precision implementation -- they are compared through the sweep's aggregate statistics instead."""
     from oracle import cport
     ta, track = oval
     E, S = 768, 2000
-    params = bgr.sweeps.pp_sweep_params(E, start=4242) if steer == "pure_pursuit" else bgr.sweeps.stanley_lqg_params(E)
-    if steer == "stanley":
-        params[:, abi.P_MU] = np.maximum(params[:, abi.P_MU], 0.9)       # keep most of the sweep on the track
-    init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.3, 0.3, E))
+    # pure pursuit: sweep rows around the reference look-ahead (Lf ~ 5.5 m); Stanley: the config-3 sweep
+    params = (bgr.sweeps.pp_sweep_params(E, start=32 * 16384 + 4242) if steer == "pure_pursuit"
+              else bgr.sweeps.stanley_lqg_params(E))
+    # the reference's dynamic model is explicit Euler at dt = 0.05: its side-slip mode is unstable below
+    # v = dt (c_f + c_r) / (2 m) ~ 3.2-3.9 m/s (DESIGN.md section 5), so dynamic-model episodes start rolling
+    init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.3, 0.3, E), v0=5.0 if model == "dynamic" else 0.0)
     cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=laps, audit=True)
     res = bgr.rollout(track, cfg, params, init)
     spec = loop.RolloutSpec(steer=steer, accel=accel, model=model, max_steps=S, laps=laps)
-    m, s, _ = cport.rollout(otrack(ta), spec, params.astype(np.float64), init)
+    p64 = params.astype(np.float64)
+    m, s, _ = cport.rollout(otrack(ta), spec, p64, init)
+    nudged = init.copy()
+    nudged[:, abi.X] += 1e-7
+    m2, _, _ = cport.rollout(otrack(ta), spec, p64, nudged)
+    well = np.hypot(m2[:, 6] - m[:, 6], m2[:, 7] - m[:, 7]) < 1e-5
     on_track = (m[:, 5] < OFF_TRACK_M) & (res.metrics[:, abi.M_MAX_ABS_LAT] < OFF_TRACK_M)
-    clean = (res.status[:, abi.S_NEAR_TIES] == 0) & on_track
-    assert on_track.mean() > 0.7 and clean.sum() > E // 2, (on_track.mean(), clean.sum())
+    unflagged = res.status[:, abi.S_NEAR_TIES] == 0
+    good = on_track & well & unflagged
+    flagged = on_track & well & ~unflagged
+    assert on_track.mean() > 0.4 and good.sum() > E // 5, (on_track.mean(), good.sum())
     cols = [abi.S_FLAGS, abi.S_STEPS, abi.S_TARGET_IND, abi.S_NEAREST_IND, abi.S_LAPS]
     mism = np.any(res.status[:, cols] != s[:, cols], axis=1)
-    assert not np.any(mism & clean), f"{(mism & clean).sum()} index mismatches without a flagged near-tie"
-    # every on-track episode, flagged or not, stays inside the tolerances (a flipped tie shifts the look-ahead
-    # target by one waypoint for one step: the closed loop absorbs it)
+    assert not np.any(mism & good), f"{(mism & good).sum()} index mismatches without a flagged near-tie"
     dpos = np.hypot(res.metrics[:, abi.M_X] - m[:, 6], res.metrics[:, abi.M_Y] - m[:, 7])
     dyaw = np.abs(res.metrics[:, abi.M_YAW] - m[:, 8])
-    assert dpos[clean].max() < POS_TOL and dyaw[clean].max() < YAW_TOL, (dpos[clean].max(), dyaw[clean].max())
-    assert np.abs(res.metrics[clean, abi.M_LAP_TIME] - m[clean, 4]).max() < LAP_TOL
-    assert np.abs(res.metrics[clean, abi.M_LAT_MEAN] - m[clean, 0]).max() < 1e-4
-    assert np.abs(res.metrics[clean, abi.M_LAT_STD] - m[clean, 1]).max() < 1e-4
-    flagged = on_track & ~clean
-    if flagged.any():
-        assert np.median(dpos[flagged]) < 10 * POS_TOL
+    # episodes without a flagged decision: the north-star tolerances (typical deviation two orders below them)
+    assert dpos[good].max() < POS_TOL and dyaw[good].max() < YAW_TOL, (dpos[good].max(), dyaw[good].max())
+    assert dpos[good].max() < 0.5 * POS_TOL and np.median(dpos[good]) < 1e-5, (dpos[good].max(), np.median(dpos[good]))
+    assert np.abs(res.metrics[good, abi.M_LAP_TIME] - m[good, 4]).max() < LAP_TOL
+    assert np.abs(res.metrics[good, abi.M_LAT_MEAN] - m[good, 0]).max() < 1e-5
+    assert np.abs(res.metrics[good, abi.M_LAT_STD] - m[good, 1]).max() < 1e-5
+    # episodes WITH a flagged decision (some threshold test came within 2e-5 m of its threshold, where the fp64
+    # oracle and the fp32 kernel may legitimately decide differently -- measured: ~1 % of them do flip, shifting the
+    # look-ahead target by one waypoint for one step, which moves the end pose by ~1.5e-3 m): most are still tight
+    if flagged.sum() >= 20:
+        assert np.quantile(dpos[flagged], 0.9) < POS_TOL, np.quantile(dpos[flagged], 0.9)
+    # the sweep's aggregate statistics agree over ALL episodes, ill-conditioned / flagged / off-track ones included
+    fin = np.isfinite(res.metrics[:, abi.M_LAT_STD]) & np.isfinite(m[:, 1])
+    assert abs(np.median(res.metrics[fin, abi.M_LAT_STD]) - np.median(m[fin, 1])) < 1e-3
+    assert abs((res.metrics[:, abi.M_MAX_ABS_LAT] < OFF_TRACK_M).mean() - (m[:, 5] < OFF_TRACK_M).mean()) < 0.01
