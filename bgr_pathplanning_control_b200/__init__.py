@@ -12,9 +12,11 @@ from .vehicle_config import Vehicle_config, conf               # noqa: F401
 from .engine import (Track, RolloutConfig, RolloutResult, MpcConfig, MpcResult, rollout, mpc_evaluate,   # noqa: F401
                      default_params, initial_states, candidate_bank, lqg_design, fp32_peak_probe,
                      last_kernel_ms, launch_count)
-from .controllers import (PurePursuitController, StanleyController, AccelerationPIDController,            # noqa: F401
+from .controllers import (PurePursuitController, StanleyController, ShadowedStanleyController, AccelerationPIDController,            # noqa: F401
                           LQGAccelerationController, MPCController, get_steering_controller,
                           normalize_angle, find_target_point, compute_control_commands)
 from .car_state import State, States                            # noqa: F401
+from .nodes import Controller, BatchedController, SimulationLogger, path_from_planner, sim_controls   # noqa: F401
+from . import metrics_calculator                                # noqa: F401
 
 __version__ = "0.1.0"

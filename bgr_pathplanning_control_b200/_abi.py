@@ -42,11 +42,12 @@ N_AGG = 8
 CONE_GUARD = 2.0
 MAX_CONES = 512
 CFG_AUDIT = 1
+CFG_STANLEY_SHADOWED = 2
 PHASE_STEER, PHASE_ACCEL, PHASE_MODEL, PHASE_ERRORS, PHASE_KAPPA_GIVEN = 1, 2, 4, 8, 16
 CMD_STEER, CMD_ACCEL, CMD_KAPPA = 0, 1, 2
 N_CMD = 4
 (C_PID_INTEGRAL, C_PID_LAST_INPUT, C_PID_HAS_LAST, C_LQG_XHAT0, C_LQG_XHAT1, C_LQG_A_PREV,
- C_STEP) = range(7)
+ C_STEP, C_PREV_STEER) = range(8)
 N_CTRL = 8
 O_STEER, O_ACCEL, O_V_DESIRED, O_KAPPA, O_E_CT, O_THETA_E, O_NEAREST_IND = range(7)
 N_OUT = 8
@@ -81,7 +82,8 @@ class RolloutCfg(C.Structure):
                 ("hit_radius", C.c_double), ("tie_eps", C.c_double),
                 ("sigma_xy", C.c_double), ("sigma_yaw", C.c_double), ("sigma_v", C.c_double),
                 ("sigma_cone", C.c_double), ("noise_seed", C.c_uint32), ("reserved1", C.c_uint32),
-                ("episode_id_base", C.c_int64)]
+                ("episode_id_base", C.c_int64), ("stanley_max_steer_rate", C.c_double),
+                ("stanley_alpha", C.c_double)]
 
 
 class MpcCfg(C.Structure):

@@ -122,6 +122,36 @@ class StanleyController:
         return np.float64(out[abi.O_STEER]), np.int64(ti)
 
 
+class ShadowedStanleyController:
+    """The SHADOWED first body of ``class StanleyController`` (core/controllers.py:234-324): adaptive gain
+    ``k / (v + k_soft)``, steering-rate limit, low-pass filter, carried ``previous_steering``.  Dead code in the
+    reference (Python keeps the later definitions, :325-385) -- offered as an explicitly labelled extra with the
+    dead code's own signature ``compute_steering(state, path, target_ind, dt)``."""
+
+    def __init__(self, k=conf.k_stanley, k_soft=conf.k_soft_stanley, max_steer_rate=np.deg2rad(30), alpha=0.5,
+                 lookahead_distance=0.0):
+        if lookahead_distance > 0:
+            raise NotImplementedError("the optional look-ahead advance (:276-281) is not built; the default is 0.0")
+        self.k, self.k_soft = k, k_soft
+        self.max_steer_rate, self.alpha = max_steer_rate, alpha
+        self.lookahead_distance = lookahead_distance
+        self.previous_steering = 0.0                                      # :250
+
+    def compute_steering(self, state, path, target_ind, dt):
+        cx, cy = _path_columns(path)
+        track = _track_for(cx, cy)
+        params = engine.default_params(1, np.float64)
+        params[0, abi.P_K_STANLEY], params[0, abi.P_K_SOFT] = self.k, self.k_soft
+        cfg = engine.RolloutConfig(steer="stanley", precision="fp64", dt=dt, stanley_shadowed=True,
+                                   stanley_max_steer_rate=self.max_steer_rate, stanley_alpha=self.alpha)
+        ctrl = np.zeros((1, abi.N_CTRL))
+        ctrl[0, abi.C_PREV_STEER] = self.previous_steering
+        out, ti = _step(track, cfg, abi.PHASE_STEER | abi.PHASE_ERRORS, params, _state_row(state), 0, ctrl,
+                        cmd=np.zeros((1, abi.N_CMD)))
+        self.previous_steering = float(ctrl[0, abi.C_PREV_STEER])        # :319
+        return np.float64(out[abi.O_STEER]), np.int64(ti)
+
+
 class AccelerationPIDController:
     """core/controllers.py:18-76; the PID arithmetic is simple-pid's with a fixed sample period
     ``conf.dt`` (the real package reads the wall clock -- see DESIGN.md 'deviations')."""

@@ -511,7 +511,7 @@ int validate_cfg(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const c
   if (cfg->max_steps < 1 || cfg->laps < 1 || cfg->laps_target < 0 || !(cfg->dt > 0.0) || !(cfg->wheelbase > 0.0) ||
       !(cfg->max_steer > 0.0) || !(cfg->max_accel >= cfg->max_decel) || cfg->hit_radius < 0.0 ||
       cfg->tie_eps < 0.0 || cfg->sigma_xy < 0.0 || cfg->sigma_yaw < 0.0 || cfg->sigma_v < 0.0 ||
-      cfg->sigma_cone < 0.0) {
+      cfg->sigma_cone < 0.0 || cfg->stanley_max_steer_rate < 0.0 || cfg->stanley_alpha < 0.0 || cfg->stanley_alpha > 1.0) {
     set_error("%s: invalid cfg (max_steps %d, laps %d, laps_target %d, dt %g, wheelbase %g, max_steer %g, ...)",
               who, cfg->max_steps, cfg->laps, cfg->laps_target, cfg->dt, cfg->wheelbase, cfg->max_steer);
     return BGR_ERR_BAD_ARG;
@@ -550,7 +550,8 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   const bool f64 = cfg->precision == BGR_PRECISION_FP64;
   const bool cones_on = cfg->hit_radius > 0.0 && track->n_cones > 0;
   const bool noise_on = cfg->sigma_xy > 0.0 || cfg->sigma_yaw > 0.0 || cfg->sigma_v > 0.0;
-  const bool full = f64 || cones_on || noise_on || want_traj || (cfg->flags & BGR_CFG_AUDIT) || sp.force_full;
+  const bool shadowed = (cfg->flags & BGR_CFG_STANLEY_SHADOWED) != 0 && cfg->steer_kind == BGR_STEER_STANLEY;
+  const bool full = f64 || cones_on || noise_on || want_traj || (cfg->flags & BGR_CFG_AUDIT) || sp.force_full || shadowed;
 
   plan->smem = f64 ? rollout_smem_bytes<double>(track->n_pad) : rollout_smem_bytes<float>(track->n_pad);
   if (plan->smem > static_cast<size_t>(di.max_smem_optin)) {
@@ -599,6 +600,11 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   A.f.sigma_yaw = static_cast<float>(cfg->sigma_yaw);
   A.f.sigma_v = static_cast<float>(cfg->sigma_v);
   A.f.sigma_cone = static_cast<float>(cfg->sigma_cone);
+  A.stanley_shadowed = shadowed ? 1 : 0;
+  A.st_rate = cfg->stanley_max_steer_rate > 0.0 ? cfg->stanley_max_steer_rate : 30.0 * 3.14159265358979323846 / 180.0;
+  A.st_alpha = cfg->stanley_alpha > 0.0 ? cfg->stanley_alpha : 0.5;
+  A.f.st_max_delta = static_cast<float>(A.st_rate * cfg->dt);
+  A.f.st_alpha = static_cast<float>(A.st_alpha);
   A.seed = cfg->noise_seed;
   A.cones_on = cones_on ? 1 : 0;
   A.noise_on = noise_on ? 1 : 0;

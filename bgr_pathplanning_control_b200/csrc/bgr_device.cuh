@@ -63,6 +63,7 @@ struct TrackView {
 struct RolloutF32 {
   float dt, inv_dt, WB, inv_WB, l_f, l_r, max_steer, tan_max_steer, max_accel, max_decel;
   float tie_eps, hit_radius, K0, K1, sigma_xy, sigma_yaw, sigma_v, sigma_cone;
+  float st_max_delta, st_alpha;   // shadowed Stanley: max_steer_rate * dt, alpha
 };
 
 struct RolloutArgs {
@@ -88,6 +89,8 @@ struct RolloutArgs {
   double lqr_k0, lqr_k1;
   double inv_dt, inv_wheelbase, tan_max_steer;  // host-computed loop invariants of the fp32 kernels
   double sigma_xy, sigma_yaw, sigma_v, sigma_cone;
+  double st_rate, st_alpha;   // shadowed Stanley variant (core/controllers.py:234-324)
+  int32_t stanley_shadowed;
   uint32_t seed;
   int32_t cones_on;
   int32_t noise_on;

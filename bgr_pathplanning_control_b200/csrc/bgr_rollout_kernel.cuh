@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
   Real pid_integ = 0, pid_last = 0;
   bool pid_has_last = false;
   Real xh0 = 0, xh1 = 0, a_prev = 0;
+  Real prev_steer = 0;   // shadowed Stanley: previous_steering (core/controllers.py:250)
   int k_gain0 = 0;
   int phases = BGR_PHASE_STEER | BGR_PHASE_ACCEL | BGR_PHASE_MODEL | BGR_PHASE_ERRORS;
   const Real K0 = static_cast<Real>(A.lqr_k0), K1 = static_cast<Real>(A.lqr_k1);
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
       xh1 = static_cast<Real>(c[BGR_C_LQG_XHAT1]);
       a_prev = static_cast<Real>(c[BGR_C_LQG_A_PREV]);
       k_gain0 = static_cast<int>(c[BGR_C_STEP]);
+      prev_steer = static_cast<Real>(c[BGR_C_PREV_STEER]);
     }
     if (A.ti_in != nullptr) {
       ti = A.ti_in[er];
@@ -290,9 +292,24 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
         j_obs = nearest(oxl, oyl, near);
         Real e_ct, theta_e;
         errors_at(j_obs, oxl, oyl, oyaw, e_ct, theta_e);
-        delta = theta_e + atan2(k_st * e_ct, ov + k_soft);           // :379
-        delta = normalize_angle(delta);                              // :380
-        delta = clampr(delta, -max_steer, max_steer);                // :381
+        bool shadowed = false;
+        if constexpr (EXTRAS) shadowed = A.stanley_shadowed != 0;
+        if (shadowed) {
+          // the SHADOWED class body (core/controllers.py:305-322): adaptive gain, rate limit, low-pass filter
+          const Real adaptive_k = k_st / (ov + k_soft);              // :305
+          delta = theta_e + atan2(adaptive_k * e_ct, Real(1));       // :308
+          delta = normalize_angle(delta);                            // :309
+          const Real max_delta = static_cast<Real>(A.st_rate) * dt;  // :312
+          delta = clampr(delta, prev_steer - max_delta, prev_steer + max_delta);   // :313
+          const Real al = static_cast<Real>(A.st_alpha);
+          delta = al * delta + (Real(1) - al) * prev_steer;          // :316
+          prev_steer = delta;                                        // :319
+          delta = clampr(delta, -max_steer, max_steer);              // :322
+        } else {
+          delta = theta_e + atan2(k_st * e_ct, ov + k_soft);         // :379
+          delta = normalize_angle(delta);                            // :380
+          delta = clampr(delta, -max_steer, max_steer);              // :381
+        }
         ti = j_obs;
         tim = j_obs;
       }
@@ -530,7 +547,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
         c[BGR_C_PID_INTEGRAL] = pid_integ; c[BGR_C_PID_LAST_INPUT] = pid_last;
         c[BGR_C_PID_HAS_LAST] = pid_has_last ? 1.0 : 0.0;
         c[BGR_C_LQG_XHAT0] = xh0; c[BGR_C_LQG_XHAT1] = xh1; c[BGR_C_LQG_A_PREV] = a_prev;
-        c[BGR_C_STEP] = static_cast<double>(k_gain0 + steps); c[7] = 0.0;
+        c[BGR_C_STEP] = static_cast<double>(k_gain0 + steps); c[BGR_C_PREV_STEER] = prev_steer;
       }
       if (A.ti_out != nullptr) A.ti_out[e] = ti;
     }

@@ -130,6 +130,9 @@ class RolloutConfig:
     sigma_cone: float = 0.0
     noise_seed: int = 0
     episode_id_base: int = 0
+    stanley_shadowed: bool = False   # the dead-code Stanley variant (core/controllers.py:234-324); labelled extra
+    stanley_max_steer_rate: float = 0.0   # 0 = reference default deg2rad(30) rad/s
+    stanley_alpha: float = 0.0            # 0 = reference default 0.5
 
     def to_struct(self):
         c = abi.RolloutCfg()
@@ -139,7 +142,8 @@ class RolloutConfig:
         except KeyError as e:
             raise ValueError(f"Unknown controller / model / precision: {e.args[0]}") from None
         c.max_steps, c.laps, c.laps_target = int(self.max_steps), int(self.laps), int(self.laps_target)
-        c.flags = abi.CFG_AUDIT if self.audit else 0
+        c.flags = (abi.CFG_AUDIT if self.audit else 0) | (abi.CFG_STANLEY_SHADOWED if self.stanley_shadowed else 0)
+        c.stanley_max_steer_rate, c.stanley_alpha = float(self.stanley_max_steer_rate), float(self.stanley_alpha)
         for k in ("dt", "wheelbase", "l_f", "l_r", "max_steer", "max_accel", "max_decel", "hit_radius", "tie_eps",
                   "sigma_xy", "sigma_yaw", "sigma_v", "sigma_cone"):
             setattr(c, k, float(getattr(self, k)))

@@ -81,3 +81,9 @@ def trajectory_frame(result, episode=0, dt=0.05, max_accel=1.5, max_decel=-2.0):
         "lateral_error": tr[:, abi.T_E_CT], "heading_error": tr[:, abi.T_THETA_E],
         "yaw_rate": r, "lateral_accel": v * r,
     }, columns=CSV_COLUMNS)
+
+
+def load_simulation_data(filename):
+    """preformance_analysis/data_loader.py:3-4."""
+    import pandas as pd
+    return pd.read_csv(filename)

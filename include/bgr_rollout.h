@@ -163,6 +163,9 @@ typedef struct bgr_track_info {
 
 #define BGR_CFG_AUDIT 1 /* run the full kernel build so that the near-tie audit channel
                            (BGR_S_NEAR_TIES / BGR_S_FIRST_TIE) is filled even without cones/noise/traj */
+#define BGR_CFG_STANLEY_SHADOWED 2 /* with BGR_STEER_STANLEY: the SHADOWED (dead-code) class body,
+                           core/controllers.py:234-324 -- adaptive gain k / (v + k_soft), steering-rate limit, low-pass
+                           filter, carried previous_steering.  A labelled extra: the live law is :336-385. */
 
 typedef struct bgr_rollout_cfg {
   int32_t steer_kind, accel_kind, model_kind, precision;
@@ -183,6 +186,9 @@ typedef struct bgr_rollout_cfg {
   uint32_t noise_seed;
   uint32_t reserved1;
   int64_t episode_id_base; /* global id of episode 0 of this call (multi-GPU shards) */
+  /* BGR_CFG_STANLEY_SHADOWED only (core/controllers.py:234): 0 = the reference defaults deg2rad(30) rad/s and 0.5 */
+  double stanley_max_steer_rate;
+  double stanley_alpha;
 } bgr_rollout_cfg_t;
 
 typedef struct bgr_mpc_cfg {
@@ -251,6 +257,7 @@ int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int
 #define BGR_C_LQG_XHAT1 4
 #define BGR_C_LQG_A_PREV 5
 #define BGR_C_STEP 6         /* LQG: index into the shared Kalman-gain sequence */
+#define BGR_C_PREV_STEER 7   /* shadowed Stanley: previous_steering (core/controllers.py:250,319) */
 #define BGR_N_CTRL 8
 /* step output row: double[BGR_N_OUT] */
 #define BGR_O_STEER 0

@@ -146,6 +146,33 @@ def stanley_steering(x, y, yaw, v, cx, cy, k=1.0, k_soft=0.1, max_steer=CONF.MAX
 
 
 # --------------------------------------------------------------------------------------
+# core/controllers.py:234-324  the SHADOWED (dead-code) Stanley variant: adaptive gain, steering-rate
+# limit, low-pass filter, carried ``previous_steering`` (stored BEFORE the final clip, :319-322).
+# Labelled extra (SURVEY.md section 8 row a2'); pinned by tests/golden/shadowed_stanley_kat.json, which
+# oracle/gen_golden_shadowed.py produces by executing the reference's own source for these lines.
+# ``lookahead_distance`` (:276-281) is kept at its default 0.0 (no look-ahead advance).
+# --------------------------------------------------------------------------------------
+SHADOWED_RATE = float(np.deg2rad(30))      # max_steer_rate default (:234)
+SHADOWED_ALPHA = 0.5                       # alpha default (:234)
+
+
+def stanley_shadowed_steering(x, y, yaw, v, cx, cy, previous_steering, dt, k=CONF.k_stanley,
+                              k_soft=CONF.k_soft_stanley, max_steer_rate=SHADOWED_RATE, alpha=SHADOWED_ALPHA,
+                              max_steer=CONF.MAX_STEER):
+    """Returns (steering, ind, new_previous_steering)."""
+    ind, theta_e, e_ct, _ = nearest_point_errors(x, y, yaw, cx, cy)             # :269-302
+    adaptive_k = k / (v + k_soft)                                                # :305
+    steering = theta_e + math.atan2(adaptive_k * e_ct, 1.0)                      # :308
+    steering = normalize_angle(steering)                                         # :309
+    max_delta = max_steer_rate * dt                                              # :312
+    steering = np.clip(steering, previous_steering - max_delta, previous_steering + max_delta)   # :313
+    steering = alpha * steering + (1 - alpha) * previous_steering                # :316
+    new_prev = float(steering)                                                   # :319
+    steering = float(np.clip(steering, -max_steer, max_steer))                   # :322
+    return steering, ind, new_prev
+
+
+# --------------------------------------------------------------------------------------
 # core/controllers.py:58-73 and :165-180  curvature -> desired speed
 # --------------------------------------------------------------------------------------
 def desired_speed(curvature, target_speed=CONF.TARGET_SPEED, k_expo=CONF.k_expo):

@@ -70,7 +70,9 @@ class NoiseSpec:
 
 @dataclass
 class RolloutSpec:
-    steer: str = "pure_pursuit"       # "pure_pursuit" | "stanley"
+    steer: str = "pure_pursuit"       # "pure_pursuit" | "stanley" | "stanley_shadowed" (dead-code variant, :234-324)
+    shadowed_rate: float = laws.SHADOWED_RATE
+    shadowed_alpha: float = laws.SHADOWED_ALPHA
     accel: str = "pid"                # "pid" | "lqg"
     model: str = "kinematic"          # "kinematic" | "dynamic"
     max_steps: int = 2000
@@ -132,6 +134,7 @@ def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode
     cone_hit = np.zeros(len(cones), dtype=bool)
 
     ti = 0
+    prev_steer = 0.0                 # StanleyController.previous_steering (:250), shadowed variant only
     prev_near = None
     lap = 0
     status = 0
@@ -165,6 +168,10 @@ def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode
         elif spec.steer == "stanley":
             delta, ti = laws.stanley_steering(ox, oy, oyaw, ov, cx_lap, cy_lap,
                                               p[P_K_STANLEY], p[P_K_SOFT], conf.MAX_STEER)
+        elif spec.steer == "stanley_shadowed":
+            delta, ti, prev_steer = laws.stanley_shadowed_steering(
+                ox, oy, oyaw, ov, cx_lap, cy_lap, prev_steer, dt, p[P_K_STANLEY], p[P_K_SOFT],
+                spec.shadowed_rate, spec.shadowed_alpha, conf.MAX_STEER)
         else:
             raise ValueError(spec.steer)
         # 3. curvature lookup (nodes/controller.py:62)
@@ -218,7 +225,7 @@ def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode
             status |= ST_NONFINITE
         if spec.steer == "pure_pursuit" and ti >= n_tot - 1:
             status |= ST_PATH_END
-        if spec.steer == "stanley" and not track.closed and ti >= n_tot - 1:
+        if spec.steer in ("stanley", "stanley_shadowed") and not track.closed and ti >= n_tot - 1:
             status |= ST_PATH_END
         if spec.laps_target > 0 and lap >= spec.laps_target:
             status |= ST_LAPS_DONE

@@ -44,6 +44,7 @@ def test_constants_match_header():
         "BGR_N_STATUS": abi.N_STATUS, "BGR_N_TRAJ": abi.N_TRAJ, "BGR_N_AGG": abi.N_AGG, "BGR_N_CMD": abi.N_CMD,
         "BGR_N_CTRL": abi.N_CTRL, "BGR_N_OUT": abi.N_OUT, "BGR_MAX_CONES": abi.MAX_CONES,
         "BGR_CONE_GUARD": abi.CONE_GUARD, "BGR_CFG_AUDIT": abi.CFG_AUDIT,
+        "BGR_CFG_STANLEY_SHADOWED": abi.CFG_STANLEY_SHADOWED, "BGR_C_PREV_STEER": abi.C_PREV_STEER,
         "BGR_P_LF": abi.P_LF, "BGR_P_KP": abi.P_KP, "BGR_P_KI": abi.P_KI, "BGR_P_KD": abi.P_KD,
         "BGR_P_TARGET_SPEED": abi.P_TARGET_SPEED, "BGR_P_K_EXPO": abi.P_K_EXPO, "BGR_P_K_STANLEY": abi.P_K_STANLEY,
         "BGR_P_K_SOFT": abi.P_K_SOFT, "BGR_P_MU": abi.P_MU, "BGR_P_C_F": abi.P_C_F, "BGR_P_C_R": abi.P_C_R,
@@ -78,7 +79,8 @@ def test_struct_layouts_match_a_c_compiler(tmp_path):
         "bgr_track_desc_t": (abi.TrackDesc, ["h_x", "n", "closed", "h_cones_xy", "n_cones", "cone_reach"]),
         "bgr_track_info_t": (abi.TrackInfo, ["n", "device", "smem_bytes_fp32", "guard_min", "ds_max"]),
         "bgr_rollout_cfg_t": (abi.RolloutCfg, ["steer_kind", "max_steps", "flags", "dt", "hit_radius", "tie_eps",
-                                                "sigma_cone", "noise_seed", "episode_id_base"]),
+                                                "sigma_cone", "noise_seed", "episode_id_base",
+                                                "stanley_max_steer_rate", "stanley_alpha"]),
         "bgr_mpc_cfg_t": (abi.MpcCfg, ["horizon", "dt", "target_speed", "q", "r", "max_steer"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{abi.HEADER_PATH}"', "int main(void){"]

@@ -272,3 +272,42 @@ def test_mpc_compute_control_cost_definition(golden, cuda_device):
         else:
             assert res.best_idx[0] == -1 and np.isinf(res.costs[0, 0])
             assert res.best_u[0, 0] == 0.0 and res.best_u[0, 1] == 0.0             # :558-562 fallback
+
+
+def test_shadowed_stanley_variant(cuda_device):
+    """SURVEY 8 row a2': the dead-code Stanley body (core/controllers.py:234-324), golden vectors produced by executing
+    the reference's own source lines (oracle/gen_golden_shadowed.py).  Single calls through the labelled drop-in class
+    (fp64 audit kernel), then the 400-step closed loop through one bgr_rollout in fp64 and in fp32."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "shadowed_stanley_kat.json")) as f:
+        g = json.load(f)
+    cx, cy = ellipse_path(720, 40.0, 20.0)
+    path = path3(cx, cy)
+    for row in g["single"]:
+        x, y, yaw, v = unhex(row["state"])
+        ctl = bgr.ShadowedStanleyController(k=unhex(row["k"]), k_soft=unhex(row["k_soft"]),
+                                            max_steer_rate=unhex(row["rate"]), alpha=unhex(row["alpha"]))
+        ctl.previous_steering = unhex(row["prev"])
+        s, ind = ctl.compute_steering(Obj(x=x, y=y, yaw=yaw, v=v), path, 0, unhex(row["dt"]))
+        assert int(ind) == row["ind"]
+        assert close(s, unhex(row["steering"]), atol=1e-13) and close(ctl.previous_steering, unhex(row["prev_out"]), atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        bgr.ShadowedStanleyController(lookahead_distance=2.0)
+    _, _, curve = golden_loop_track()
+    L = g["loop"]
+    want = np.asarray(unhex(L["traj"]))
+    track = bgr.Track(cx, cy, curve, closed=True)
+    params = bgr.default_params(1)
+    params[0, abi.P_K_STANLEY], params[0, abi.P_K_SOFT] = bgr.conf.k_stanley, bgr.conf.k_soft_stanley
+    init = np.asarray(unhex(L["init"]), dtype=np.float64).reshape(1, 6)
+    for precision, pos_tol, yaw_tol in (("fp64", 5e-6, 5e-7), ("fp32", 1e-3, 1e-4)):
+        cfg = bgr.RolloutConfig(steer="stanley", accel="pid", model="dynamic", precision=precision, max_steps=len(want),
+                                stanley_shadowed=True)
+        res = bgr.rollout(track, cfg, params, init, traj=True)
+        tr = res.traj[0]
+        assert list(tr[:, abi.T_TARGET_IND].astype(int)) == L["ti"]
+        assert np.hypot(tr[:, abi.T_X] - want[:, 0], tr[:, abi.T_Y] - want[:, 1]).max() < pos_tol
+        assert np.abs(tr[:, abi.T_YAW] - want[:, 2]).max() < yaw_tol
+        assert np.abs(tr[:, abi.T_STEER] - np.asarray(unhex(L["steer"]))).max() < 20 * yaw_tol

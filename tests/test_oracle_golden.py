@@ -226,3 +226,36 @@ def test_mpc_cost_definition(golden):
         best, a, s, c = laws.mpc_select(cb, fb, u[None])
         if feas:
             assert same(a, unhex(row["ret_accel"])) and same(s, unhex(row["ret_steer"]))
+
+
+def test_shadowed_stanley_variant():
+    """core/controllers.py:234-324 (dead code, executed from the reference's own source via ast by
+    oracle/gen_golden_shadowed.py) vs the oracle restatement: single calls and a 400-step closed loop."""
+    import json
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "shadowed_stanley_kat.json")) as f:
+        g = json.load(f)
+    d = {k: unhex(v) for k, v in g["defaults"].items()}
+    assert (d["k"], d["k_soft"], d["alpha"], d["lookahead_distance"]) == (laws.CONF.k_stanley, laws.CONF.k_soft_stanley,
+                                                                         laws.SHADOWED_ALPHA, 0.0)
+    assert same(d["max_steer_rate"], laws.SHADOWED_RATE)
+    cx, cy = ellipse(720, 40.0, 20.0)
+    for row in g["single"]:
+        x, y, yaw, v = unhex(row["state"])
+        s, ind, prev = laws.stanley_shadowed_steering(x, y, yaw, v, cx, cy, unhex(row["prev"]), unhex(row["dt"]),
+                                                      unhex(row["k"]), unhex(row["k_soft"]), unhex(row["rate"]),
+                                                      unhex(row["alpha"]))
+        assert ind == row["ind"]
+        assert same(s, unhex(row["steering"])) and same(prev, unhex(row["prev_out"])), row
+    th = np.linspace(0, 2 * np.pi, 720, endpoint=False)
+    curve = (40.0 * 20.0) / ((40.0 * np.sin(th)) ** 2 + (20.0 * np.cos(th)) ** 2) ** 1.5
+    L = g["loop"]
+    want = np.asarray(unhex(L["traj"]))
+    p = loop.default_params()
+    p[loop.P_K_STANLEY], p[loop.P_K_SOFT] = laws.CONF.k_stanley, laws.CONF.k_soft_stanley
+    spec = loop.RolloutSpec(steer="stanley_shadowed", accel="pid", model="dynamic", max_steps=len(want))
+    out = loop.rollout_episode(loop.Track(cx, cy, curve, closed=True), spec, p, unhex(L["init"]))
+    assert list(out["ti"]) == L["ti"]
+    assert_same(out["traj"], want, "traj")
+    assert_same(out["steer"], unhex(L["steer"]), "steer")
+    assert_same(out["accel"], unhex(L["accel"]), "accel")
