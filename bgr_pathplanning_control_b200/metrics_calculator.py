@@ -47,7 +47,7 @@ def _column_mean_std(col):
     produced by ``trajectory_frame``)."""
     import torch
 
-    a = col.to_numpy() if hasattr(col, "to_numpy") else np.asarray(col)
+    a = np.array(col.to_numpy() if hasattr(col, "to_numpy") else col, dtype=np.float64)   # writable copy
     if not torch.cuda.is_available():
         raise RuntimeError("metrics_calculator needs a CUDA device (no CPU fallback)")
     t = torch.as_tensor(a, dtype=torch.float64, device="cuda")

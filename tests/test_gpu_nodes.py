@@ -33,8 +33,9 @@ def test_controller_node_update_protocol(cuda_device):
     state = [float(ta.x[0]), float(ta.y[0]) + 0.2, 0.05, 2.0, 0.0, 0.0]
     ti = 0
     for k in range(40):
-        data["car_state"] = Obj(x=state[0], y=state[1], yaw=state[2], v=state[3], v_linear=1, v_angular=2, a_angular=3,
-                                a_linear=4, timestamp=0.05 * k)
+        data["car_state"] = Obj(x=state[0], y=state[1], yaw=state[2], v=state[3], v_linear=1, v_angular=2,
+                                a_angular=Obj(x_val=0.1, y_val=0.2), a_linear=Obj(x_val=0.3, y_val=0.4),
+                                timestamp=0.05 * k)
         data["current_time"] = 0.05 * k
         node.update(data)
         want_s, ti = laws.pure_pursuit_steering(state[0], state[1], state[2], cx, cy, ti, bgr.conf.LOOKAHEAD_DISTANCE)
@@ -50,6 +51,7 @@ def test_controller_node_update_protocol(cuda_device):
         state = laws.kinematic_bicycle_step(state, want_s, want_a, bgr.conf.dt)
     hist = data["states"]
     assert hist is node.states and len(hist.x) == 40 and len(hist.steering) == 40 and len(hist.v_log) == 40
+    assert hist.a_longitudinal[0] == 0.1 and hist.a_lateral[0] == 0.2     # a_linear=car_state.a_angular (:74, sic)
     assert hist.y[0] == -(float(ta.y[0]) + 0.2)                                   # the logged state is y-flipped (:43-45)
     # missing inputs: warn and return, nothing appended (:37-41)
     node.update({"cx": cx})
