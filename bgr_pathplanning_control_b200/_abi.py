@@ -43,6 +43,7 @@ CONE_GUARD = 2.0
 MAX_CONES = 512
 CFG_AUDIT = 1
 CFG_STANLEY_SHADOWED = 2
+MPC_EXPLICIT_ROLLOUT = 1
 PHASE_STEER, PHASE_ACCEL, PHASE_MODEL, PHASE_ERRORS, PHASE_KAPPA_GIVEN = 1, 2, 4, 8, 16
 CMD_STEER, CMD_ACCEL, CMD_KAPPA = 0, 1, 2
 N_CMD = 4
@@ -89,7 +90,8 @@ class RolloutCfg(C.Structure):
 class MpcCfg(C.Structure):
     _fields_ = [("horizon", C.c_int32), ("precision", C.c_int32), ("dt", C.c_double), ("wheelbase", C.c_double),
                 ("target_speed", C.c_double), ("q", C.c_double * 4), ("r", C.c_double * 2),
-                ("max_accel", C.c_double), ("max_decel", C.c_double), ("max_steer", C.c_double)]
+                ("max_accel", C.c_double), ("max_decel", C.c_double), ("max_steer", C.c_double),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BgrError(RuntimeError):

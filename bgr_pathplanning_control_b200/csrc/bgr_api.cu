@@ -1068,9 +1068,16 @@ extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, 
   DeviceInfo di;
   BGR_TRY(device_info(track->device, &di));
   Scratch sc(stream);
-  unsigned long long* d_packed;
-  BGR_TRY(sc.get(&d_packed, static_cast<size_t>(n_episodes)));
-  BGR_CUDA(cudaMemsetAsync(d_packed, 0xff, static_cast<size_t>(n_episodes) * sizeof(unsigned long long), stream));
+  const bool explicit_rollout = cfg->precision == BGR_PRECISION_FP64 || (cfg->flags & BGR_MPC_EXPLICIT_ROLLOUT);
+  // one scratch block: [packed argmin accumulators | candidate statistics | episode coefficients]
+  const size_t b_packed = (static_cast<size_t>(n_episodes) * sizeof(unsigned long long) + 255) & ~size_t(255);
+  const size_t b_cand = explicit_rollout ? 0 : (mpc_cand_bytes(n_candidates) + 255) & ~size_t(255);
+  const size_t b_epi = explicit_rollout ? 0 : mpc_epi_bytes(n_episodes);
+  unsigned char* d_scratch;
+  BGR_TRY(sc.get(&d_scratch, b_packed + b_cand + b_epi));
+  unsigned long long* d_packed = reinterpret_cast<unsigned long long*>(d_scratch);
+  if (explicit_rollout)
+    BGR_CUDA(cudaMemsetAsync(d_packed, 0xff, static_cast<size_t>(n_episodes) * sizeof(unsigned long long), stream));
   MpcArgs A;
   std::memset(&A, 0, sizeof(A));
   A.trk = track->view();
@@ -1094,8 +1101,14 @@ extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, 
   A.r1 = cfg->r[1];
   BGR_TRY(ensure_events(track->device));
   BGR_CUDA(cudaEventRecord(g_last.start, stream));
-  BGR_CUDA(launch_mpc(A, cfg->precision, stream, di.sm_count));
-  count_launch();
+  if (explicit_rollout) {
+    // audit: explicit stage-by-stage rollout, reference operation order (fp64), or the fp32 explicit rollout
+    BGR_CUDA(launch_mpc(A, cfg->precision, stream, di.sm_count));
+    count_launch();
+  } else {
+    BGR_CUDA(launch_mpc_factored(A, d_scratch + b_packed, d_scratch + b_packed + b_cand, stream, di.sm_count));
+    count_launch(2);
+  }
   BGR_CUDA(cudaEventRecord(g_last.stop, stream));
   g_last.valid = true;
   BGR_CUDA(launch_mpc_finalize(d_packed, d_bank, cfg->horizon, n_episodes, static_cast<float>(cfg->max_accel),

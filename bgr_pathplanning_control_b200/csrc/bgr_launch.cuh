@@ -51,6 +51,11 @@ struct MpcArgs {
 };
 
 cudaError_t launch_mpc(const MpcArgs& A, int precision, cudaStream_t stream, int sm_count);
+// factored evaluator (production): candidate statistics + episode coefficients + 4 FMAs per pair
+cudaError_t launch_mpc_factored(const MpcArgs& A, void* scratch_cand, void* scratch_epi, cudaStream_t stream,
+                                int sm_count);
+size_t mpc_cand_bytes(int K);
+size_t mpc_epi_bytes(long long E);
 cudaError_t launch_mpc_finalize(const unsigned long long* packed, const float* bank, int H, long long n_episodes,
                                 float max_accel, float max_decel, float max_steer, float* best_u, float* best_cost,
                                 int32_t* best_idx, cudaStream_t stream);

@@ -4,7 +4,16 @@
 // scoring K candidate control sequences per episode with the reference's own cost (:545, :548) under
 // its own linearised dynamics (:522-527) and feasibility rule (:536), and taking the cheapest one.
 //
-// Mapping: ONE CANDIDATE PER THREAD.  A thread loads its candidate's H x (accel, steer) controls ONCE
+// Two evaluators:
+//   * PRODUCTION (precision fp32 in the ABI; evaluated in fp64): the FACTORED form.  Under the reference's
+//     linearisation x and y do not depend on the controls (:523-524) and yaw / v are affine in PREFIX SUMS of the
+//     control sequence (:525-526), so the whole (H + 1)-stage cost of candidate c for episode e is
+//         J(e, c) = C0_e + G_c + C1_e SS_c + C2_e SS2_c + C3_e SA_c ,   feasible  <=>  v0_e >= vreq_c
+//     with five per-candidate statistics (one pass over the bank) and four per-episode coefficients (one pass over
+//     the states): 4 fused multiply-adds per (episode, candidate) pair instead of H stages.  Same cost, same argmin.
+//   * AUDIT (precision fp64): the explicit stage-by-stage rollout below, in the reference's operation order.
+//
+// Mapping of the explicit rollout: ONE CANDIDATE PER THREAD.  A thread loads its candidate's H x (accel, steer) controls ONCE
 // into registers and then walks over a strided list of episodes, so the candidate bank is read from
 // HBM/L2 exactly once per CTA row and the inner loop touches only registers plus one broadcast
 // shared-memory word per stage (the per-episode, candidate-independent x/y cost: :523-524 make x and y
@@ -142,6 +151,159 @@ __global__ void __launch_bounds__(kMpcThreads) mpc_kernel(const __grid_constant_
     // stage[b] is rewritten only after the NEXT iteration's barrier, so thread 0's read above is safe
   }
 }
+
+
+// ================================================================================================
+// factored evaluator (production)
+// ================================================================================================
+struct CandStats {   // per candidate: statistics of the prefix sums of its control sequence
+  double G;          // sum_k (r0 a_k^2 + r1 s_k^2)  +  q3 * sum_{k=0..H} A_k^2          (:545 control cost + speed part)
+  double SS, SS2;    // sum_{k=0..H} S_k,  sum S_k^2       S_k = dt * sum_{i<k} steer_i   (yaw_k = yaw0 + v0/WB * S_k, :525)
+  double SA;         // sum_{k=0..H} A_k                   A_k = dt * sum_{i<k} accel_i   (v_k = v0 + A_k, :526)
+  double vreq;       // -min_{k=1..H} A_k : feasible (v_k >= 0 for all k, :536) iff v0 >= vreq
+};
+struct EpiCoef {     // per episode
+  double C0, C1, C2, C3, v0;
+};
+
+__device__ __forceinline__ void candidate_stats(const float* __restrict__ bank, int K, int H, double dt, double r0,
+                                                double r1, double q3, CandStats* __restrict__ out, int c) {
+  if (c >= K) return;
+  const float2* u = reinterpret_cast<const float2*>(bank) + static_cast<size_t>(c) * H;
+  double A = 0.0, S = 0.0, U = 0.0, SA = 0.0, SA2 = 0.0, SS = 0.0, SS2 = 0.0, Amin = 0.0;
+  bool first = true;
+  for (int k = 0; k < H; ++k) {          // stage k sees the prefix sums of the controls before it
+    const float2 uk = __ldg(u + k);
+    const double a = uk.x, s = uk.y;
+    U += r0 * a * a + r1 * s * s;
+    A = A + a * dt;                       // v_{k+1} - v0, accumulated like :526
+    S = S + s * dt;                       // (yaw_{k+1} - yaw0) / (v0 / WB), :525
+    SA += A; SA2 += A * A;                // stages 1..H (stage 0 contributes A_0 = 0)
+    SS += S; SS2 += S * S;
+    Amin = first ? A : fmin(Amin, A);
+    first = false;
+  }
+  CandStats r;
+  r.G = U + q3 * SA2;
+  r.SS = SS; r.SS2 = SS2; r.SA = SA;
+  r.vreq = -Amin;
+  out[c] = r;
+}
+
+__device__ __forceinline__ void episode_coef(const MpcArgs& A, EpiCoef* __restrict__ out, long long e) {
+  if (e >= A.n_episodes) return;
+  A.packed[e] = ~0ull;                                             // argmin accumulator of this episode
+  const double* s = A.state + e * 4;
+  const double x0 = s[0], y0 = s[1], yaw0 = s[2], v0 = s[3];
+  const double cos_t = cos(yaw0), sin_t = sin(yaw0);               // :514-515
+  const int n = A.trk.n;
+  const int start = A.ref_start[e];
+  int len = A.ref_len != nullptr ? A.ref_len[e] : (A.trk.closed ? 0x3fffffff : n - start);
+  if (len < 1) len = 1;
+  double sx = x0, sy = y0, XY = 0.0;
+  for (int t = 0; t <= A.H; ++t) {                                  // stages 0..H-1 and the terminal term (:548)
+    int k_ref = t < A.H ? t : A.H - 1;
+    if (k_ref >= len) k_ref = len - 1;
+    long long idx = static_cast<long long>(start) + k_ref;
+    if (A.trk.closed) idx %= n;
+    else if (idx > n - 1) idx = n - 1;
+    const double2 p = A.trk.xy_d[idx];
+    const double ex = sx - p.x, ey = sy - p.y;
+    XY += A.q0 * ex * ex + A.q1 * ey * ey;
+    sx = sx + v0 * cos_t * A.dt;                                    // :523
+    sy = sy + v0 * sin_t * A.dt;                                    // :524
+  }
+  const double cyw = v0 / A.wheelbase;                              // yaw_k = yaw0 + cyw * S_k
+  const double ev0 = v0 - A.target_speed;
+  const double n1 = static_cast<double>(A.H + 1);
+  EpiCoef r;
+  r.C0 = XY + A.q2 * n1 * yaw0 * yaw0 + A.q3 * n1 * ev0 * ev0;
+  r.C1 = 2.0 * A.q2 * yaw0 * cyw;
+  r.C2 = A.q2 * cyw * cyw;
+  r.C3 = 2.0 * A.q3 * ev0;
+  r.v0 = v0;
+  out[e] = r;
+}
+
+// one launch: the first `cand_blocks` CTAs compute candidate statistics, the rest episode coefficients
+__global__ void __launch_bounds__(128) mpc_prepare_kernel(const __grid_constant__ MpcArgs A, int cand_blocks,
+                                                          CandStats* __restrict__ cand, EpiCoef* __restrict__ epi) {
+  if (static_cast<int>(blockIdx.x) < cand_blocks) {
+    candidate_stats(A.bank, A.K, A.H, A.dt, A.r0, A.r1, A.q3, cand, blockIdx.x * 128 + threadIdx.x);
+  } else {
+    episode_coef(A, epi, static_cast<long long>(blockIdx.x - cand_blocks) * 128 + threadIdx.x);
+  }
+}
+
+// One EPISODE per lane (its coefficients in registers), warp w of the CTA takes candidates w, w + 8, ... ; the
+// candidate statistics are staged in shared memory in chunks and read as warp-wide broadcasts, so the inner loop is
+// 4 fp64 FMAs + one compare per (episode, candidate) pair with no cross-thread traffic at all.  Each thread keeps
+// the first minimum of its slice (ascending candidate index, strict <); the 8 slices of an episode meet in one
+// 64-bit atomicMin on (cost bits << 32 | index): order independent, lowest index wins exact ties like np.argmin.
+constexpr int kFactThreads = 256;
+constexpr int kFactSlices = kFactThreads / 32;
+constexpr int kFactChunk = 1024;                 // candidates staged per pass: 1024 x 40 B = 40 KB => 5 CTAs per SM
+
+__global__ void __launch_bounds__(kFactThreads) mpc_factored_kernel(const CandStats* __restrict__ cand,
+                                                                    const EpiCoef* __restrict__ epi, int K,
+                                                                    long long n_episodes,
+                                                                    unsigned long long* __restrict__ packed,
+                                                                    float* __restrict__ costs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CandStats* s_c = reinterpret_cast<CandStats*>(smem_raw);
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const long long e = static_cast<long long>(blockIdx.x) * 32 + lane;
+  const bool evalid = e < n_episodes;
+  const EpiCoef ec = epi[evalid ? e : 0];
+  float best = INFINITY;
+  int best_i = -1;
+  for (int c0 = 0; c0 < K; c0 += kFactChunk) {
+    const int nc = min(kFactChunk, K - c0);
+    __syncthreads();
+    {  // coalesced copy of the chunk (5 doubles per candidate)
+      const double* src = reinterpret_cast<const double*>(cand + c0);
+      double* dst = reinterpret_cast<double*>(s_c);
+      for (int i = threadIdx.x; i < nc * 5; i += kFactThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = slice; c < nc; c += kFactSlices) {
+      const CandStats cs = s_c[c];
+      // two independent FMA pairs (shorter dependency chain than a 4-deep Horner form)
+      const double J = fma(ec.C1, cs.SS, ec.C0 + cs.G) + fma(ec.C3, cs.SA, ec.C2 * cs.SS2);
+      float costf = static_cast<float>(J);
+      if (!(ec.v0 >= cs.vreq) || !(costf == costf)) costf = INFINITY;           // infeasible (:536) / NaN
+      costf = fmaxf(costf, 0.0f);                                               // round-off below an exact zero
+      if (costs != nullptr && evalid) costs[static_cast<size_t>(e) * K + c0 + c] = costf;
+      if (costf < best) {
+        best = costf;
+        best_i = c0 + c;
+      }
+    }
+  }
+  if (evalid && best < INFINITY)
+    atomicMin(packed + e, (static_cast<unsigned long long>(__float_as_uint(best)) << 32) | static_cast<uint32_t>(best_i));
+}
+
+cudaError_t launch_mpc_factored(const MpcArgs& A, void* scratch_cand, void* scratch_epi, cudaStream_t stream,
+                                int sm_count) {
+  (void)sm_count;
+  CandStats* cand = static_cast<CandStats*>(scratch_cand);
+  EpiCoef* epi = static_cast<EpiCoef*>(scratch_epi);
+  const int cand_blocks = (A.K + 127) / 128;
+  const unsigned epi_blocks = static_cast<unsigned>((A.n_episodes + 127) / 128);
+  mpc_prepare_kernel<<<cand_blocks + epi_blocks, 128, 0, stream>>>(A, cand_blocks, cand, epi);
+  const size_t smem = static_cast<size_t>(A.K < kFactChunk ? A.K : kFactChunk) * sizeof(CandStats);
+  cudaError_t err = cudaFuncSetAttribute(mpc_factored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  const unsigned grid = static_cast<unsigned>((A.n_episodes + 31) / 32);
+  mpc_factored_kernel<<<grid, kFactThreads, smem, stream>>>(cand, epi, A.K, A.n_episodes, A.packed, A.costs);
+  return cudaGetLastError();
+}
+
+size_t mpc_cand_bytes(int K) { return static_cast<size_t>(K) * sizeof(CandStats); }
+size_t mpc_epi_bytes(long long E) { return static_cast<size_t>(E) * sizeof(EpiCoef); }
 
 // packed (cost bits, index) -> (acceleration, steering) with the return convention of :565-568
 __global__ void mpc_finalize_kernel(const unsigned long long* __restrict__ packed, const float* __restrict__ bank,

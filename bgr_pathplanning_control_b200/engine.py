@@ -336,9 +336,11 @@ class MpcConfig:
     max_accel: float = conf.MAX_ACCEL
     max_decel: float = conf.MAX_DECEL
     max_steer: float = conf.MAX_STEER
+    explicit_rollout: bool = False   # fp32 stage-by-stage rollout instead of the factored evaluator
 
     def to_struct(self):
         c = abi.MpcCfg()
+        c.flags = abi.MPC_EXPLICIT_ROLLOUT if self.explicit_rollout else 0
         c.horizon, c.precision = int(self.horizon), _PRECISION[self.precision]
         c.dt, c.wheelbase, c.target_speed = float(self.dt), float(self.wheelbase), float(self.target_speed)
         for i in range(4):

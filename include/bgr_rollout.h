@@ -191,15 +191,19 @@ typedef struct bgr_rollout_cfg {
   double stanley_alpha;
 } bgr_rollout_cfg_t;
 
+#define BGR_MPC_EXPLICIT_ROLLOUT 1 /* bgr_mpc_cfg_t.flags: score candidates by the explicit stage-by-stage rollout
+                                     even in fp32 (default: the algebraically factored evaluator) */
 typedef struct bgr_mpc_cfg {
   int32_t horizon;         /* MPCController.N  core/controllers.py:472,587 */
-  int32_t precision;
+  int32_t precision;       /* BGR_PRECISION_FP64 = explicit rollout in the reference's operation order */
   double dt;               /* MPCController.dt */
   double wheelbase;        /* conf.WB, :525 */
   double target_speed;     /* conf.TARGET_SPEED, :540 */
   double q[4];             /* diag Q :483 */
   double r[2];             /* diag R :484 */
   double max_accel, max_decel, max_steer; /* :565-566 */
+  int32_t flags;           /* BGR_MPC_* */
+  int32_t reserved;
 } bgr_mpc_cfg_t;
 
 /* ---- library ---- */

@@ -81,7 +81,7 @@ def test_struct_layouts_match_a_c_compiler(tmp_path):
         "bgr_rollout_cfg_t": (abi.RolloutCfg, ["steer_kind", "max_steps", "flags", "dt", "hit_radius", "tie_eps",
                                                 "sigma_cone", "noise_seed", "episode_id_base",
                                                 "stanley_max_steer_rate", "stanley_alpha"]),
-        "bgr_mpc_cfg_t": (abi.MpcCfg, ["horizon", "dt", "target_speed", "q", "r", "max_steer"]),
+        "bgr_mpc_cfg_t": (abi.MpcCfg, ["horizon", "dt", "target_speed", "q", "r", "max_steer", "flags"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{abi.HEADER_PATH}"', "int main(void){"]
     for cname, (_, fl) in fields.items():

@@ -105,3 +105,27 @@ def test_mpc_controller_drop_in(cuda_device):
     assert np.isclose(ctrl.last_cost, wc, rtol=2e-5)
     assert np.isclose(a, wa, atol=1e-6) and np.isclose(s, ws, atol=1e-6)
     assert -bgr.conf.MAX_STEER <= s <= bgr.conf.MAX_STEER and bgr.conf.MAX_DECEL <= a <= bgr.conf.MAX_ACCEL
+
+
+def test_factored_evaluator_equals_explicit_rollout(cuda_device):
+    """The production evaluator scores a candidate from five prefix-sum statistics and four per-episode coefficients
+    (the reference's linearised dynamics make the (H + 1)-stage cost affine in them); the explicit
+    stage-by-stage rollout (fp32 with the flag, fp64 audit) is the same function: equal costs to fp32 round-off,
+    identical feasibility, identical argmin wherever the optimum is decided beyond round-off."""
+    ta = bgr.tracks.stadium_oval(1024)
+    track = bgr.Track.from_arrays(ta)
+    E, K, H = 256, 2048, 30
+    states, ref_start = bgr.sweeps.mpc_states(ta, E)
+    states[:6, 3] = [0.0, 0.01, 0.03, 0.06, 0.1, 0.2]
+    bank = bgr.candidate_bank(K, H)
+    fact = bgr.mpc_evaluate(track, bgr.MpcConfig(horizon=H), states, ref_start, bank, return_costs=True)
+    expl = bgr.mpc_evaluate(track, bgr.MpcConfig(horizon=H, explicit_rollout=True), states, ref_start, bank,
+                            return_costs=True)
+    audit = bgr.mpc_evaluate(track, bgr.MpcConfig(horizon=H, precision="fp64"), states, ref_start, bank,
+                             return_costs=True)
+    fin = np.isfinite(audit.costs)
+    assert np.array_equal(fin, np.isfinite(fact.costs)) and np.array_equal(fin, np.isfinite(expl.costs))
+    np.testing.assert_allclose(fact.costs[fin], audit.costs[fin], rtol=3e-7)      # both evaluated in fp64
+    np.testing.assert_allclose(expl.costs[fin], audit.costs[fin], rtol=2e-5)      # fp32 accumulation over 31 stages
+    assert (fact.best_idx == audit.best_idx).mean() > 0.99
+    assert np.array_equal(fact.best_cost, fact.costs[np.arange(E), fact.best_idx])
