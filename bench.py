@@ -33,6 +33,18 @@ import numpy as np  # noqa: E402
 METRIC = "closed-loop sim-steps/sec (episodes x steps)"
 UNIT = "sim-steps/s"
 
+# ncu --set full --clock-control none, one capture of the step kernel per change (profiles/r1_final/*.json)
+NCU_EVIDENCE = {
+    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 89.2,
+                 "sm_throughput_pct": 88.0, "pipe_fma_pct": 38.2, "pipe_alu_pct": 47.7, "pipe_xu_pct": 40.3,
+                 "pipe_fp64_pct": 6.4, "fp32_thread_inst_per_cycle_pct_of_peak": 27.5, "dram_throughput_pct": 0.08,
+                 "warp_inst_per_warp_step": 337.4, "registers": 64, "dram_bytes_per_launch": 171.3e6},
+    "stanley_lqg": {"file": "profiles/r1_final/ncu_full_stanley_lqg_dynamic.json", "issue_slots_busy_pct": 88.6,
+                    "sm_throughput_pct": 87.5, "pipe_fma_pct": 37.2, "pipe_alu_pct": 51.7, "pipe_xu_pct": 43.1,
+                    "pipe_fp64_pct": 6.4, "fp32_thread_inst_per_cycle_pct_of_peak": 26.7, "dram_throughput_pct": 0.08,
+                    "warp_inst_per_warp_step": 362.1, "registers": 64},
+}
+
 WORKLOADS = {
     # name: (steer, accel, model, laps of the unrolled path, BASELINE config it is)
     "pp_sweep": ("pure_pursuit", "pid", "kinematic", 8,
@@ -356,10 +368,14 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_tflops, "unit": "TFLOP/s",
-                "frac": achieved_tflops / fp32_tflops, "traffic": None,
+                "frac": achieved_tflops / fp32_tflops,
+                "traffic": (NCU_EVIDENCE.get(args.workload) or {}).get("dram_bytes_per_launch"),
                 "peak_source": "bgr_fp32_peak_probe (FFMA chains, measured in this run); MEASURED_PEAKS.json has no fp32 row",
                 "flops_per_sim_step": flops_step, "kernel_ms_avg": k_ms, "kernel_ms_last": kernel_ms_last,
                 "sim_steps_per_launch": steps_per_launch,
+                # what ncu measured for this kernel build (one --set full capture per change, profiles/r1_final/):
+                # the kernel is bound by INSTRUCTION ISSUE, not by DRAM (0.08 %) or tensor (0 %)
+                "ncu": NCU_EVIDENCE.get(args.workload),
                 "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
                         "bytes_per_launch": bytes_launch, "peak_source": peaks_src},
             },
