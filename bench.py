@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="pp_sweep", choices=list(WORKLOADS) + ["mpc"])
+    ap.add_argument("--workload", default="pp_sweep", choices=list(WORKLOADS) + ["mpc", "skidpad_mc"])
     ap.add_argument("--episodes", type=int, default=1 << 20, help="episodes per GPU per step")
     ap.add_argument("--sim-steps", type=int, default=2000, help="closed-loop control steps per episode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -247,6 +247,8 @@ def run_b200(args):
 
     if args.workload == "mpc":
         return run_mpc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, barrier)
+    if args.workload == "skidpad_mc":
+        return run_skidpad_mc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, barrier)
 
     steer, accel, model, laps, desc = WORKLOADS[args.workload]
     E, S = args.episodes, args.sim_steps
@@ -386,6 +388,112 @@ def run_b200(args):
             v, cores, sample = cpu_sample(args.workload, S, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                     "cpu": cpu_model()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_skidpad_mc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, barrier):
+    """BASELINE config 5 (secondary bench line): skidpad figure-eight, mixed-controller Monte Carlo with Philox pose
+    noise and perturbed cones; episodes are grouped by controller kind on the host (three homogeneous launches per
+    step); the final per-episode metric gather + aggregate reduction goes through NCCL."""
+    kinds = [("pure_pursuit", "pid", "kinematic"), ("stanley", "pid", "kinematic"), ("stanley", "lqg", "dynamic")]
+    per = max(256, (args.episodes // 2) // len(kinds) // 256 * 256)       # 512 Ki episodes per GPU in total by default
+    S = min(args.sim_steps, 1500)
+    ta = bgr.tracks.skidpad(2048)
+    track = bgr.Track.from_arrays(ta, device=local, cone_reach=4.0)
+    noise = dict(sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1, sigma_cone=0.05, noise_seed=20261022, hit_radius=0.5)
+    jobs = []
+    for g, (steer, accel, model) in enumerate(kinds):
+        lo = (rank * len(kinds) + g) * per
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=1, episode_id_base=lo, **noise)
+        init = bgr.initial_states(ta, per, index=0, v0=5.0 if model == "dynamic" else 0.0)
+        init[:, abi.YAW] = 0.0
+        params = bgr.sweeps.monte_carlo_params(per, start=lo)
+        out = bgr.RolloutResult(torch.empty((per, abi.N_METRICS), dtype=torch.float32, device=dev),
+                                torch.empty((per, abi.N_STATUS), dtype=torch.int32, device=dev), None,
+                                torch.empty(abi.N_AGG, dtype=torch.float64, device=dev))
+        jobs.append((cfg, torch.from_numpy(params).to(dev), torch.from_numpy(init).to(dev), out, params, init))
+
+    def step():
+        return [bgr.rollout(track, j[0], j[1], j[2], aggregate=True, out=j[3]) for j in jobs]
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = bgr.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    done = torch.zeros((), dtype=torch.float64, device=dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        for r in step():
+            done += r.aggregate[abi.A_STEPS]
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = bgr.launch_count() - launches0
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    tot = done.clone().reshape(1)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total, total_steps = float(t.item()), float(tot.item())
+    gather_ms = None
+    if world > 1:
+        m = torch.cat([j[3].metrics for j in jobs])
+        s = torch.cat([j[3].status for j in jobs])
+        agg = torch.from_numpy(bgr.sharding.combine_aggregates([j[3].aggregate.cpu().numpy() for j in jobs])).to(dev)
+        bgr.sharding.gather_results(m, s, agg, m.shape[0] * world)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        m_all, s_all, agg_all = bgr.sharding.gather_results(m, s, agg, m.shape[0] * world)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
+        assert float(agg_all[abi.A_EPISODES]) == m.shape[0] * world
+    # e2e: host buffers
+    w0 = time.perf_counter()
+    e2e_steps = 0.0
+    for _ in range(args.steps):
+        for j in jobs:
+            r = bgr.rollout(track, j[0], j[4], j[5], aggregate=True)
+            e2e_steps += float(r.aggregate[abi.A_STEPS])
+    e2e_s = time.perf_counter() - w0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    se = torch.tensor([e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(se, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        fp32_tflops, _ = bgr.fp32_peak_probe(local)
+        flops = np.mean([rf.flops_per_step(*k) for k in kinds])
+        ach = total_steps / world * flops / (ms_total * 1e-3) / 1e12
+        hits = sum(float(j[3].aggregate[abi.A_CONE_HITS]) for j in jobs)
+        line = {
+            "metric": METRIC, "value": total_steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 laws + f64 integrators (x, y, yaw, v) and metric sums",
+            "data": "synthetic",
+            "config": {"workload": "config 5: skidpad figure-eight, mixed-controller Monte Carlo with noisy pose / cone "
+                                   "perturbations (Philox4x32-10), NCCL metric gather", "episodes_per_gpu": per * len(kinds),
+                       "kinds": ["+".join(k) for k in kinds], "sim_steps_cap": S, "track": "skidpad n=2048, 45 cones",
+                       "cone_hits_last_step_rank0": hits, "parallelism": f"episode sharding x{world}",
+                       "l2": "state lives in registers; 112 B in + 88 B out per episode"},
+            "clocks": clocks,
+            "e2e": {"value": float(se.item()) / float(te.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": per * len(kinds) * 112, "d2h_bytes_per_step": per * len(kinds) * 88 + 3 * 64},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_tflops, "unit": "TFLOP/s", "frac": ach / fp32_tflops,
+                         "traffic": None, "note": "full kernel build (cones + noise): 128 registers, 2 CTAs per SM"},
+        }
+        if gather_ms is not None:
+            line["gather_ms"] = gather_ms
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
