@@ -404,6 +404,13 @@ def run_skidpad_mc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, bar
     ta = bgr.tracks.skidpad(2048)
     track = bgr.Track.from_arrays(ta, device=local, cone_reach=4.0)
     noise = dict(sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1, sigma_cone=0.05, noise_seed=20261022, hit_radius=0.5)
+    for k in os.environ.get("BGR_MC_OFF", "").split(","):      # diagnostic: switch parts of the Monte Carlo off
+        if k == "cone_noise":
+            noise["sigma_cone"] = 0.0
+        elif k == "cones":
+            noise["hit_radius"] = 0.0
+        elif k == "pose_noise":
+            noise.update(sigma_xy=0.0, sigma_yaw=0.0, sigma_v=0.0)
     jobs = []
     for g, (steer, accel, model) in enumerate(kinds):
         lo = (rank * len(kinds) + g) * per

@@ -141,10 +141,22 @@ static void kalman_gains_host(double dt, int n_steps, double* out /*[n][2]*/) {
 // of slab(j) /\ H_i nearest to w_j lies on the bisector line of (w_i, w_j) restricted to the slab:
 // a 1-D interval problem.  O(n^2) on the host, once per track.
 // ------------------------------------------------------------------------------------------------
+// Rival lists extend the guard to tracks that run close to themselves (skidpad: the second lap of a circle lies on
+// top of the first, so guard(j) ~ 0 all along it).  rivals(j) = every non-neighbour i with
+// dist(w_j, slab(j) /\ H_i) < reach.  For p in slab(j) with |p - w_j| < reach the global argmin i* either is j or
+// satisfies p in H_{i*}, hence dist(w_j, slab(j) /\ H_{i*}) <= |p - w_j| < reach, i.e. i* is in rivals(j): the exact
+// argmin is the best of {j} U rivals(j) -- a handful of evaluations instead of a scan over all n waypoints.
+constexpr int kMaxRivals = 1024;   // longer lists fall back to the exact scan (a list is still cheaper than 32 scans)
+
 static void compute_guards(const std::vector<double>& x, const std::vector<double>& y, bool closed,
-                           std::vector<double>* guard) {
+                           std::vector<double>* guard, std::vector<int32_t>* rival_first,
+                           std::vector<int32_t>* rival_list) {
   const int n = static_cast<int>(x.size());
   guard->assign(n, 0.0);
+  rival_first->assign(n + 1, 0);
+  rival_list->clear();
+  const double reach2 = kRivalReach * kRivalReach;
+  std::vector<int32_t> mine;
   for (int j = 0; j < n; ++j) {
     int nb[2];
     int n_nb = 0;
@@ -165,36 +177,48 @@ static void compute_guards(const std::vector<double>& x, const std::vector<doubl
     }
     double best2 = INFINITY;
     if (degenerate) best2 = 0.0;
-    for (int i = 0; i < n && best2 > 0.0; ++i) {
+    mine.clear();
+    bool lists_ok = !degenerate;
+    for (int i = 0; i < n; ++i) {
       if (i == j || (n_nb > 0 && i == nb[0]) || (n_nb > 1 && i == nb[1])) continue;
       const double wx = x[i] - x[j], wy = y[i] - y[j];
       const double D2 = wx * wx + wy * wy;
-      if (D2 == 0.0) {  // coincident with a non-neighbour: only the exact scan can apply the index tie rule
-        best2 = 0.0;
-        break;
+      double cand2;
+      if (D2 == 0.0) {  // coincident with a non-neighbour: the index tie rule decides, the rival check applies it
+        cand2 = 0.0;
+      } else {
+        if (0.25 * D2 >= best2 && 0.25 * D2 >= reach2) continue;
+        const double D = std::sqrt(D2);
+        // bisector: q(t) = m + t u, m - w_j = (wx, wy) / 2, u = (-wy, wx) / D
+        const double ux = -wy / D, uy = wx / D;
+        double lo = -INFINITY, hi = INFINITY;
+        bool empty = false;
+        for (int s = 0; s < n_nb; ++s) {
+          // (q - w_j) . e_s <= |e_s|^2 / 2   <=>   t (u . e_s) <= |e_s|^2 / 2 - (m - w_j) . e_s
+          const double a = ux * ex[s] + uy * ey[s];
+          const double b = eh[s] - 0.5 * (wx * ex[s] + wy * ey[s]);
+          if (a > 0.0) hi = std::min(hi, b / a);
+          else if (a < 0.0) lo = std::max(lo, b / a);
+          else if (b < 0.0) empty = true;
+        }
+        if (empty || lo > hi) continue;
+        double t = 0.0;
+        if (lo > 0.0) t = lo;
+        else if (hi < 0.0) t = hi;
+        cand2 = 0.25 * D2 + t * t;
       }
-      if (0.25 * D2 >= best2) continue;
-      const double D = std::sqrt(D2);
-      // bisector: q(t) = m + t u, m - w_j = (wx, wy) / 2, u = (-wy, wx) / D
-      const double ux = -wy / D, uy = wx / D;
-      double lo = -INFINITY, hi = INFINITY;
-      bool empty = false;
-      for (int s = 0; s < n_nb; ++s) {
-        // (q - w_j) . e_s <= |e_s|^2 / 2   <=>   t (u . e_s) <= |e_s|^2 / 2 - (m - w_j) . e_s
-        const double a = ux * ex[s] + uy * ey[s];
-        const double b = eh[s] - 0.5 * (wx * ex[s] + wy * ey[s]);
-        if (a > 0.0) hi = std::min(hi, b / a);
-        else if (a < 0.0) lo = std::max(lo, b / a);
-        else if (b < 0.0) empty = true;
+      best2 = std::min(best2, cand2);
+      if (cand2 < reach2) {
+        if (static_cast<int>(mine.size()) < kMaxRivals) mine.push_back(i);
+        else lists_ok = false;
       }
-      if (empty || lo > hi) continue;
-      double t = 0.0;
-      if (lo > 0.0) t = lo;
-      else if (hi < 0.0) t = hi;
-      best2 = std::min(best2, 0.25 * D2 + t * t);
     }
     (*guard)[j] = std::sqrt(best2);  // may be +inf (e.g. a straight line)
+    (*rival_first)[j] = static_cast<int32_t>(rival_list->size());
+    if (lists_ok) rival_list->insert(rival_list->end(), mine.begin(), mine.end());
+    else (*rival_first)[j] = -static_cast<int32_t>(rival_list->size()) - 1;   // negative: no usable list here
   }
+  (*rival_first)[n] = static_cast<int32_t>(rival_list->size());
 }
 
 }  // namespace bgr
@@ -268,6 +292,8 @@ extern "C" void bgr_track_destroy(bgr_track_t* t) {
   cudaFree(t->xy_d);
   cudaFree(t->attr_d);
   cudaFree(t->guard2);
+  cudaFree(t->rival_range);
+  cudaFree(t->rival_list);
   cudaFree(t->cone_range);
   cudaFree(t->cone_list);
   cudaFree(t->cones);
@@ -350,7 +376,8 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     }
     t->path_yaw[j] = std::atan2(dy, dx);
   }
-  compute_guards(t->x, t->y, t->closed != 0, &t->guard_radius);
+  std::vector<int32_t> rival_first, rival_list;
+  compute_guards(t->x, t->y, t->closed != 0, &t->guard_radius, &rival_first, &rival_list);
 
   t->ds_min = INFINITY;
   t->ds_max = 0.0;
@@ -388,6 +415,23 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     guard2[j] = static_cast<float>(std::min(g * g, 1e30));
   }
 
+  // rival lists as (first, count) per waypoint; count < 0 = no usable list (exact scan instead)
+  std::vector<int2> rival_range(n);
+  for (int j = 0; j < n; ++j) {
+    const bool ok = rival_first[j] >= 0;
+    const int first = ok ? rival_first[j] : -rival_first[j] - 1;
+    int next = rival_first[j + 1];
+    if (next < 0) next = -next - 1;
+    rival_range[j] = make_int2(first, ok ? next - first : -1);
+    if (ok) {
+      t->rival_total += next - first;
+      t->rival_max = std::max(t->rival_max, next - first);
+    } else {
+      ++t->rival_unlisted;
+    }
+  }
+  if (rival_list.empty()) rival_list.push_back(0);
+
   // cone candidate lists: cones within cone_reach of waypoint j
   std::vector<int32_t> cone_range(n, 0), cone_list;
   std::vector<double2> cones(t->n_cones);
@@ -420,6 +464,8 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   if (rc == BGR_OK) rc = upload(&t->xy_d, xy_d);
   if (rc == BGR_OK) rc = upload(&t->attr_d, attr_d);
   if (rc == BGR_OK) rc = upload(&t->guard2, guard2);
+  if (rc == BGR_OK) rc = upload(&t->rival_range, rival_range);
+  if (rc == BGR_OK) rc = upload(&t->rival_list, rival_list);
   if (rc == BGR_OK && t->n_cones > 0) {
     rc = upload(&t->cone_range, cone_range);
     if (rc == BGR_OK) rc = upload(&t->cone_list, cone_list);
@@ -449,6 +495,9 @@ extern "C" int bgr_track_info(const bgr_track_t* t, bgr_track_info_t* out) {
   out->guard_median = t->guard_median;
   out->ds_min = t->ds_min;
   out->ds_max = t->ds_max;
+  out->rival_total = t->rival_total;
+  out->rival_max = t->rival_max;
+  out->rival_unlisted = t->rival_unlisted;
   return BGR_OK;
 }
 

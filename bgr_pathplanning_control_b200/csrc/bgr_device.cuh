@@ -19,6 +19,8 @@ namespace bgr {
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kTwoPi = 2.0 * 3.14159265358979323846;
 constexpr int kRolloutThreads = 256;
+constexpr double kRivalReach = 2.5;                                   // [m] rival lists are complete up to here (host)
+constexpr double kRivalAccept = kRivalReach * (1.0 - 1e-4) - 1e-4;   // [m] ... and trusted up to here (device)
 
 struct alignas(32) D4 {
   double x, y, z, w;
@@ -48,6 +50,8 @@ struct TrackView {
   const double2* xy_d;
   const D4* attr_d;
   const float* guard2;
+  const int2* rival_range;    // [n] (first, count) into rival_list; count < 0: none
+  const int32_t* rival_list;
   const int32_t* cone_range;  // [n] (first << 10) | count  into cone_list
   const int32_t* cone_list;
   const double2* cones;       // [n_cones]

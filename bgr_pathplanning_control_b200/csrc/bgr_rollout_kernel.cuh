@@ -216,7 +216,25 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
             }
           }
           const Real dj2 = kF64 ? dj * dj : dj;
-          global = !(dj2 < static_cast<Real>(s_guard2[j]));
+          if (!(dj2 < static_cast<Real>(s_guard2[j]))) {
+            // outside the plain guard: best of {j} U rivals(j) within the lists' reach, else the exact scan
+            const int2 rr = __ldg(A.trk.rival_range + j);
+            if (rr.y >= 0 && dj2 < static_cast<Real>(kRivalAccept * kRivalAccept)) {
+              for (int q = 0; q < rr.y; ++q) {
+                const int i = __ldg(A.trk.rival_list + rr.x + q);
+                const Real di = dist(i, lx, ly);
+                if (di < dj || (di == dj && i < j)) {
+                  d_nb = fmin(d_nb, dj);
+                  dj = di;
+                  j = i;
+                } else {
+                  d_nb = fmin(d_nb, di);
+                }
+              }
+            } else {
+              global = true;
+            }
+          }
         }
         if (global) {
           ++fallbacks;

@@ -16,6 +16,8 @@ struct bgr_track {
   double2* xy_d = nullptr;
   bgr::D4* attr_d = nullptr;
   float* guard2 = nullptr;
+  int2* rival_range = nullptr;     // per waypoint (first, count) into rival_list; count < 0: no usable list
+  int32_t* rival_list = nullptr;
   int32_t* cone_range = nullptr;
   int32_t* cone_list = nullptr;
   double2* cones = nullptr;
@@ -31,10 +33,13 @@ struct bgr_track {
   // host copies
   std::vector<double> x, y, kappa, path_yaw, guard_radius;
   double ds_min = 0, ds_max = 0, guard_min = 0, guard_median = 0;
+  long long rival_total = 0;
+  int rival_max = 0, rival_unlisted = 0;
 
   bgr::TrackView view() const {
     bgr::TrackView v;
     v.xy_f = xy_f; v.attr_f = attr_f; v.xy_d = xy_d; v.attr_d = attr_d; v.guard2 = guard2;
+    v.rival_range = rival_range; v.rival_list = rival_list;
     v.cone_range = cone_range; v.cone_list = cone_list; v.cones = cones;
     v.n = n; v.n_pad = n_pad; v.closed = closed; v.n_cones = n_cones;
     v.ds_max = static_cast<float>(ds_max);

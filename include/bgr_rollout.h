@@ -159,6 +159,9 @@ typedef struct bgr_track_info {
   int64_t smem_bytes_fp32, smem_bytes_fp64;
   double guard_min, guard_median; /* exactness-guard radii of the windowed nearest search [m] */
   double ds_min, ds_max;          /* waypoint spacing [m] */
+  int64_t rival_total;            /* total length of the rival lists of the nearest search */
+  int32_t rival_max;              /* longest list */
+  int32_t rival_unlisted;         /* waypoints without a usable list (exact scan outside their guard) */
 } bgr_track_info_t;
 
 #define BGR_CFG_AUDIT 1 /* run the full kernel build so that the near-tie audit channel

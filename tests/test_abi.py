@@ -77,7 +77,8 @@ def test_struct_layouts_match_a_c_compiler(tmp_path):
     src = tmp_path / "probe.c"
     fields = {
         "bgr_track_desc_t": (abi.TrackDesc, ["h_x", "n", "closed", "h_cones_xy", "n_cones", "cone_reach"]),
-        "bgr_track_info_t": (abi.TrackInfo, ["n", "device", "smem_bytes_fp32", "guard_min", "ds_max"]),
+        "bgr_track_info_t": (abi.TrackInfo, ["n", "device", "smem_bytes_fp32", "guard_min", "ds_max", "rival_total",
+                                               "rival_max", "rival_unlisted"]),
         "bgr_rollout_cfg_t": (abi.RolloutCfg, ["steer_kind", "max_steps", "flags", "dt", "hit_radius", "tie_eps",
                                                 "sigma_cone", "noise_seed", "episode_id_base",
                                                 "stanley_max_steer_rate", "stanley_alpha"]),
