@@ -236,6 +236,11 @@ __device__ __forceinline__ Real u01_24(uint32_t r) {
   return (static_cast<Real>(r >> 8) + Real(0.5)) * Real(1.0 / 16777216.0);
 }
 
+// sin / cos of 2 pi u for u in (0, 1).  float: sincospif has an exact argument reduction (no 2 pi rounding, no
+// Payne-Hanek path); double: the oracle's own expression cos(2 pi u), sin(2 pi u)
+__device__ __forceinline__ void sincos_2pi(float u, float* s, float* c) { sincospif(2.0f * u, s, c); }
+__device__ __forceinline__ void sincos_2pi(double u, double* s, double* c) { sincos_r(kTwoPi * u, s, c); }
+
 // two Box-Muller pairs -> four standard normals (oracle/philox.py:gaussians4)
 template <typename Real>
 __device__ __forceinline__ void gaussians4(U4 r, Real z[4]) {
@@ -243,10 +248,10 @@ __device__ __forceinline__ void gaussians4(U4 r, Real z[4]) {
   Real ra = sqrt(Real(-2.0) * log(ua));
   Real rc = sqrt(Real(-2.0) * log(uc));
   Real s, c;
-  sincos_r(Real(kTwoPi) * ub, &s, &c);
+  sincos_2pi(ub, &s, &c);
   z[0] = ra * c;
   z[1] = ra * s;
-  sincos_r(Real(kTwoPi) * ud, &s, &c);
+  sincos_2pi(ud, &s, &c);
   z[2] = rc * c;
   z[3] = rc * s;
 }

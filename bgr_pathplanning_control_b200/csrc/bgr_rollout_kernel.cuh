@@ -407,7 +407,10 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
             const int c = listed ? __ldg(A.trk.cone_list + first + i) : i;
             const double2 cp = __ldg(A.trk.cones + c);
             Real cdx = static_cast<Real>(cp.x - X), cdy = static_cast<Real>(cp.y - Y);
-            if (A.sigma_cone > 0.0) {
+            // per-(cone, episode) perturbation: only drawn when the unperturbed cone is within reach of the hit
+            // circle (8 sigma per component: P < 1e-15 of mattering)
+            const Real far_ = hr + Real(11.4) * static_cast<Real>(A.sigma_cone);
+            if (A.sigma_cone > 0.0 && cdx * cdx + cdy * cdy <= far_ * far_) {
               Real z[4];
               gaussians4<Real>(philox4x32_10(static_cast<uint32_t>(c), kStreamCone, 0u, 0u, A.seed,
                                              static_cast<uint32_t>(A.episode_id_base + e)), z);
