@@ -670,12 +670,6 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   // LQG: LQR gain + the shared, data-independent Kalman gain sequence (uploaded once per (dt, length) and kept
   // on the track handle until it is destroyed)
   if (cfg->accel_kind == BGR_ACCEL_LQG) {
-    double K[2];
-    lqr_gain_host(cfg->dt, K);
-    A.lqr_k0 = K[0];
-    A.lqr_k1 = K[1];
-    A.f.K0 = static_cast<float>(K[0]);
-    A.f.K1 = static_cast<float>(K[1]);
     int kf_len = cfg->max_steps;
     if (sp.ctrl_in != nullptr) kf_len = 4096;  // single-step API: index carried by the caller, clamped in-kernel
     std::lock_guard<std::mutex> lock(track->kf_mu);
@@ -692,6 +686,7 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
       bgr_track::KfTable t;
       t.dt = cfg->dt;
       t.len = len;
+      lqr_gain_host(cfg->dt, t.K);             // Riccati iteration: once per (track, dt), not per call
       BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.d_gain), gains.size() * sizeof(double)));
       BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.d_gain_f), gains_f.size() * sizeof(float2)));
       BGR_CUDA(cudaMemcpy(t.d_gain, gains.data(), gains.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -699,6 +694,10 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
       track->kf_tables.push_back(t);
       hit = &track->kf_tables.back();
     }
+    A.lqr_k0 = hit->K[0];
+    A.lqr_k1 = hit->K[1];
+    A.f.K0 = static_cast<float>(hit->K[0]);
+    A.f.K1 = static_cast<float>(hit->K[1]);
     A.kf_gain = hit->d_gain;
     A.kf_gain_f = hit->d_gain_f;
     A.kf_len = hit->len;

@@ -25,6 +25,7 @@ struct bgr_track {
   struct KfTable {
     double dt = 0;
     int len = 0;
+    double K[2] = {0, 0};   // LQR gain of control.dlqr for this dt
     double* d_gain = nullptr;
     float2* d_gain_f = nullptr;
   };
