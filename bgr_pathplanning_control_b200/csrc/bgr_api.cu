@@ -341,9 +341,9 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   int rc = device_info(device, &di);
   if (rc != BGR_OK) return rc;
   const int n_pad = (n + 12 + 3) & ~3;   // fp32 xy table: 4 cyclic entries in front, >= 8 behind (bgr_rollout_f32.cuh)
-  if (rollout_smem_bytes<float>(n_pad) > static_cast<size_t>(di.max_smem_optin)) {
+  if (rollout_smem_bytes_xy_only(n_pad) > static_cast<size_t>(di.max_smem_optin)) {
     set_error("bgr_track_create: %d waypoints need %zu B of shared memory per CTA, device offers %d", n,
-              rollout_smem_bytes<float>(n_pad), di.max_smem_optin);
+              rollout_smem_bytes_xy_only(n_pad), di.max_smem_optin);
     return BGR_ERR_TOO_LARGE;
   }
 
@@ -603,6 +603,12 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   const bool full = f64 || cones_on || noise_on || want_traj || (cfg->flags & BGR_CFG_AUDIT) || sp.force_full || shadowed;
 
   plan->smem = f64 ? rollout_smem_bytes<double>(track->n_pad) : rollout_smem_bytes<float>(track->n_pad);
+  bool attr_in_smem = true;
+  if (!f64) {
+    static const int force = [] { const char* e = std::getenv("BGR_ATTR_IN_SMEM"); return e ? std::atoi(e) : -1; }();
+    attr_in_smem = force >= 0 ? force != 0 : plan->smem <= kSmemAllTablesLimit;
+    if (!attr_in_smem) plan->smem = rollout_smem_bytes_xy_only(track->n_pad);
+  }
   if (plan->smem > static_cast<size_t>(di.max_smem_optin)) {
     set_error("bgr_rollout: track needs %zu B of shared memory per CTA in this precision, device offers %d",
               plan->smem, di.max_smem_optin);
@@ -656,6 +662,7 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   A.f.st_alpha = static_cast<float>(A.st_alpha);
   A.seed = cfg->noise_seed;
   A.cones_on = cones_on ? 1 : 0;
+  A.attr_in_smem = attr_in_smem ? 1 : 0;
   A.noise_on = noise_on ? 1 : 0;
   A.phases = sp.phases;
   A.ctrl_in = sp.ctrl_in;

@@ -97,6 +97,7 @@ struct RolloutArgs {
   int32_t stanley_shadowed;
   uint32_t seed;
   int32_t cones_on;
+  int32_t attr_in_smem;   // fp32 kernels: attr / guard tables staged in shared memory (short tracks) or read via L1
   int32_t noise_on;
   // single-step plumbing (EXTRAS kernels only; all nullptr for a rollout)
   int32_t phases;

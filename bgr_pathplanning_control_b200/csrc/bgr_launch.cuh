@@ -26,6 +26,12 @@ BGR_FOR_ALL_LAWS(BGR_DECLARE_LAUNCH, float, false)
 BGR_FOR_ALL_LAWS(BGR_DECLARE_LAUNCH, float, true)
 BGR_FOR_ALL_LAWS(BGR_DECLARE_LAUNCH, double, true)
 
+// fp32 kernels on long tracks stage only the xy table (8 B per waypoint)
+__host__ __device__ constexpr size_t rollout_smem_bytes_xy_only(int n_pad) {
+  return static_cast<size_t>(n_pad) * sizeof(float2) + 64 + kRolloutThreads / 32 * BGR_N_AGG * sizeof(double);
+}
+constexpr size_t kSmemAllTablesLimit = 56 * 1024;   // up to here 4 CTAs per SM still fit with every table staged
+
 template <typename Real>
 __host__ __device__ constexpr size_t rollout_smem_bytes(int n_pad) {
   return static_cast<size_t>(n_pad) * (sizeof(typename RT<Real>::R2) + sizeof(typename RT<Real>::R4) + sizeof(float)) +

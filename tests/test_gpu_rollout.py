@@ -265,7 +265,7 @@ def test_edge_cases(oval, cuda_device):
     res = bgr.rollout(track, bgr.RolloutConfig(max_steps=50), bgr.default_params(1), bad)
     assert res.status[0, abi.S_FLAGS] & abi.ST_NONFINITE
     # a centreline too long for the shared-memory staging budget is refused, not truncated
-    big = 20000
+    big = 40000
     th = np.linspace(0, 2 * np.pi, big, endpoint=False)
     with pytest.raises(abi.BgrError) as ei:
         bgr.Track(500 * np.cos(th), 500 * np.sin(th), None, closed=True)
@@ -361,3 +361,22 @@ def test_parity_at_scale_against_the_c_twin(oval, steer, accel, model, laps):
     fin = np.isfinite(res.metrics[:, abi.M_LAT_STD]) & np.isfinite(m[:, 1])
     assert abs(np.median(res.metrics[fin, abi.M_LAT_STD]) - np.median(m[fin, 1])) < 1e-3
     assert abs((res.metrics[:, abi.M_MAX_ABS_LAT] < OFF_TRACK_M).mean() - (m[:, 5] < OFF_TRACK_M).mean()) < 0.01
+
+
+def test_long_track_stages_only_the_xy_table(cuda_device):
+    """n = 6000 waypoints: the attr / guard tables no longer fit next to xy at 4 CTAs per SM, so the kernel stages xy
+    only and reads the rest through L1 -- same results as the fp64 oracle, and identical to a short-track run of the
+    same geometry forced onto that path (BGR_ATTR_IN_SMEM is read once per process, so compare against the oracle)."""
+    n = 6000
+    th = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    ta = bgr.tracks.TrackArrays(60 * np.cos(th), 35 * np.sin(th),
+                                60 * 35 / (60 ** 2 * np.sin(th) ** 2 + 35 ** 2 * np.cos(th) ** 2) ** 1.5, True)
+    track = bgr.Track.from_arrays(ta)
+    assert track.info()["smem_bytes_fp32"] > 56 * 1024
+    E = 8
+    params = bgr.default_params(E)
+    params[:, abi.P_LF] = np.linspace(4.0, 7.0, E)
+    for steer, accel, model in (("pure_pursuit", "pid", "kinematic"), ("stanley", "lqg", "dynamic")):
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=600, laps=2)
+        init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.3, 0.3, E), v0=5.0)
+        compare(ta, track, cfg, params, init, range(0, E, 2))
