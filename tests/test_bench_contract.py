@@ -1,0 +1,57 @@
+"""bench.py prints ONE JSON line with the keys the driver's contract names -- checked for the CPU reference arm here
+(no GPU needed) and for the GPU arm on a B200 with a shrunken workload."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def run_bench(*args, env=None):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                         cwd=ROOT, timeout=900, env={**os.environ, **(env or {})})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_reference_arm_json_line():
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--sim-steps", "150")
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"].startswith("closed-loop sim-steps/sec") and d["unit"] == "sim-steps/s"
+    assert d["value"] > 1e3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "episodes" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, cwd=ROOT, timeout=60, env={**os.environ, "RANK": "1"})
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload", ["pp_sweep", "stanley_lqg", "mpc", "skidpad_mc"])
+def test_gpu_arm_json_line(workload):
+    d = run_bench("--workload", workload, "--steps", "3", "--warmup", "3", "--episodes", "16384", "--sim-steps", "300",
+                  "--cpu-seconds", "1")
+    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks"} <= set(d) or workload == "mpc"
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3
+    assert d["gpu_launches"] >= 3
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and 0 < r["frac"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    if workload in ("pp_sweep", "stanley_lqg"):
+        assert e["value"] <= d["value"] * 1.05                 # host copies are inside the e2e region
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+        assert d["clocks"]["sm_max_mhz"] and d["roofline"]["hbm"]["peak"] > 1000
+        assert d["config"]["episodes_per_gpu"] == 16384
