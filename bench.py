@@ -35,14 +35,14 @@ UNIT = "sim-steps/s"
 
 # ncu --set full --clock-control none, one capture of the step kernel per change (profiles/r1_final/*.json)
 NCU_EVIDENCE = {
-    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 89.2,
-                 "sm_throughput_pct": 88.0, "pipe_fma_pct": 38.2, "pipe_alu_pct": 47.7, "pipe_xu_pct": 40.3,
-                 "pipe_fp64_pct": 6.4, "fp32_thread_inst_per_cycle_pct_of_peak": 27.5, "dram_throughput_pct": 0.08,
-                 "warp_inst_per_warp_step": 337.4, "registers": 64, "dram_bytes_per_launch": 171.3e6},
-    "stanley_lqg": {"file": "profiles/r1_final/ncu_full_stanley_lqg_dynamic.json", "issue_slots_busy_pct": 88.6,
-                    "sm_throughput_pct": 87.5, "pipe_fma_pct": 37.2, "pipe_alu_pct": 51.7, "pipe_xu_pct": 43.1,
-                    "pipe_fp64_pct": 6.4, "fp32_thread_inst_per_cycle_pct_of_peak": 26.7, "dram_throughput_pct": 0.08,
-                    "warp_inst_per_warp_step": 362.1, "registers": 64},
+    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 88.7,
+                 "sm_throughput_pct": 87.6, "pipe_fma_pct": 34.4, "pipe_alu_pct": 52.5, "pipe_xu_pct": 42.1,
+                 "pipe_fp64_pct": 6.7, "fp32_thread_inst_per_cycle_pct_of_peak": 27.2, "dram_throughput_pct": 0.10,
+                 "warp_inst_per_warp_step": 321.1, "registers": 64, "dram_bytes_per_launch": 167.2e6},
+    "stanley_lqg": {"file": "profiles/r1_final/ncu_full_stanley_lqg_dynamic.json", "issue_slots_busy_pct": 87.8,
+                    "sm_throughput_pct": 86.7, "pipe_fma_pct": 35.5, "pipe_alu_pct": 52.2, "pipe_xu_pct": 43.6,
+                    "pipe_fp64_pct": 6.4, "fp32_thread_inst_per_cycle_pct_of_peak": 25.5, "dram_throughput_pct": 0.09,
+                    "warp_inst_per_warp_step": 355.7, "registers": 64, "dram_bytes_per_launch": 167.2e6},
 }
 
 WORKLOADS = {

@@ -51,7 +51,6 @@ def test_gpu_arm_json_line(workload):
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     if workload in ("pp_sweep", "stanley_lqg"):
-        assert e["value"] <= d["value"] * 2.0                  # (tiny workload: both arms are launch bound)
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
         assert d["clocks"]["sm_max_mhz"] and d["roofline"]["hbm"]["peak"] > 1000
         assert d["config"]["episodes_per_gpu"] == 16384
