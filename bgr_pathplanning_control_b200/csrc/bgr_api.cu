@@ -150,13 +150,13 @@ constexpr int kMaxRivals = 1024;   // longer lists fall back to the exact scan (
 
 static void compute_guards(const std::vector<double>& x, const std::vector<double>& y, bool closed,
                            std::vector<double>* guard, std::vector<int32_t>* rival_first,
-                           std::vector<int32_t>* rival_list) {
+                           std::vector<int2>* rival_list) {
   const int n = static_cast<int>(x.size());
   guard->assign(n, 0.0);
   rival_first->assign(n + 1, 0);
   rival_list->clear();
   const double reach2 = kRivalReach * kRivalReach;
-  std::vector<int32_t> mine;
+  std::vector<std::pair<double, int32_t>> mine;   // (squared reach-in distance, waypoint)
   for (int j = 0; j < n; ++j) {
     int nb[2];
     int n_nb = 0;
@@ -209,13 +209,22 @@ static void compute_guards(const std::vector<double>& x, const std::vector<doubl
       }
       best2 = std::min(best2, cand2);
       if (cand2 < reach2) {
-        if (static_cast<int>(mine.size()) < kMaxRivals) mine.push_back(i);
+        if (static_cast<int>(mine.size()) < kMaxRivals) mine.emplace_back(cand2, i);
         else lists_ok = false;
       }
     }
     (*guard)[j] = std::sqrt(best2);  // may be +inf (e.g. a straight line)
     (*rival_first)[j] = static_cast<int32_t>(rival_list->size());
-    if (lists_ok) rival_list->insert(rival_list->end(), mine.begin(), mine.end());
+    if (lists_ok) {
+      // sorted by the distance from w_j at which the rival can first win: the device walks a list only up to the
+      // car's own distance from w_j (stored 1e-4 m short, which covers the fp32 rounding of waypoints and offsets)
+      std::sort(mine.begin(), mine.end());
+      for (const auto& m : mine) {
+        const double c = std::max(0.0, std::sqrt(m.first) - 1e-4);
+        const float c2 = std::nextafterf(static_cast<float>(c * c), 0.0f);
+        rival_list->push_back(make_int2(m.second, __builtin_bit_cast(int, c2)));
+      }
+    }
     else (*rival_first)[j] = -static_cast<int32_t>(rival_list->size()) - 1;   // negative: no usable list here
   }
   (*rival_first)[n] = static_cast<int32_t>(rival_list->size());
@@ -376,7 +385,8 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     }
     t->path_yaw[j] = std::atan2(dy, dx);
   }
-  std::vector<int32_t> rival_first, rival_list;
+  std::vector<int32_t> rival_first;
+  std::vector<int2> rival_list;
   compute_guards(t->x, t->y, t->closed != 0, &t->guard_radius, &rival_first, &rival_list);
 
   t->ds_min = INFINITY;
@@ -430,7 +440,7 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
       ++t->rival_unlisted;
     }
   }
-  if (rival_list.empty()) rival_list.push_back(0);
+  if (rival_list.empty()) rival_list.push_back(make_int2(0, 0));
 
   // cone candidate lists: cones within cone_reach of waypoint j
   std::vector<int32_t> cone_range(n, 0), cone_list;

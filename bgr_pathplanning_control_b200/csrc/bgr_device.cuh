@@ -51,7 +51,7 @@ struct TrackView {
   const D4* attr_d;
   const float* guard2;
   const int2* rival_range;    // [n] (first, count) into rival_list; count < 0: none
-  const int32_t* rival_list;
+  const int2* rival_list;     // (waypoint, bits of its squared reach-in distance), ascending per list
   const int32_t* cone_range;  // [n] (first << 10) | count  into cone_list
   const int32_t* cone_list;
   const double2* cones;       // [n_cones]

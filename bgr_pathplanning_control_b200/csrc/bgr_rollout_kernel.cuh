@@ -220,8 +220,11 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
             // outside the plain guard: best of {j} U rivals(j) within the lists' reach, else the exact scan
             const int2 rr = __ldg(A.trk.rival_range + j);
             if (rr.y >= 0 && dj2 < static_cast<Real>(kRivalAccept * kRivalAccept)) {
+              const Real d_own2 = dj2;
               for (int q = 0; q < rr.y; ++q) {
-                const int i = __ldg(A.trk.rival_list + rr.x + q);
+                const int2 ent = __ldg(A.trk.rival_list + rr.x + q);
+                if (static_cast<Real>(__int_as_float(ent.y)) > d_own2) break;   // sorted: nobody further can win
+                const int i = ent.x;
                 const Real di = dist(i, lx, ly);
                 if (di < dj || (di == dj && i < j)) {
                   d_nb = fmin(d_nb, dj);

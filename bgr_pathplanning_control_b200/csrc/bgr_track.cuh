@@ -17,7 +17,7 @@ struct bgr_track {
   bgr::D4* attr_d = nullptr;
   float* guard2 = nullptr;
   int2* rival_range = nullptr;     // per waypoint (first, count) into rival_list; count < 0: no usable list
-  int32_t* rival_list = nullptr;
+  int2* rival_list = nullptr;      // (waypoint, float bits of the squared distance from w_j at which it can first win)
   int32_t* cone_range = nullptr;
   int32_t* cone_list = nullptr;
   double2* cones = nullptr;
