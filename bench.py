@@ -114,6 +114,31 @@ def cpu_sample(workload, sim_steps, seconds, cores=None):
     return total / busy, cores, desc
 
 
+def c_twin_sample(workload, sim_steps, episodes_per_core=4):
+    """The same sample through the plain-C oracle twin (oracle/c, OpenMP over episodes): a compiled restatement of
+    the reference algorithm -- its O(N) hypot argmin per step keeps it at the Python loop's rate."""
+    try:
+        import bgr_pathplanning_control_b200 as bgr
+        from oracle import cport, loop
+        if not cport.available():
+            return None
+        steer, accel, model, laps, _ = WORKLOADS[workload]
+        cores = len(os.sched_getaffinity(0))
+        E = cores * episodes_per_core
+        ta = bgr.tracks.stadium_oval(1024)
+        params = (bgr.sweeps.pp_sweep_params(E) if workload == "pp_sweep" else bgr.sweeps.stanley_lqg_params(E))
+        init = bgr.initial_states(ta, E, v0=5.0 if model == "dynamic" else 0.0)
+        spec = loop.RolloutSpec(steer=steer, accel=accel, model=model, max_steps=sim_steps, laps=laps)
+        t0 = time.perf_counter()
+        _, st, _ = cport.rollout(loop.Track(ta.x, ta.y, ta.kappa, True, ta.cones), spec, params.astype(np.float64), init,
+                                 threads=cores)
+        dt = time.perf_counter() - t0
+        return {"value": float(st[:, 1].sum()) / dt, "unit": UNIT, "cores": cores,
+                "sample": f"{E} episodes x {sim_steps} steps, OpenMP over episodes, {dt:.1f} s"}
+    except Exception as exc:            # the C twin is optional context, never a reason to lose the bench line
+        return {"unavailable": str(exc)[:200]}
+
+
 def cpu_model():
     try:
         with open("/proc/cpuinfo") as f:
@@ -387,7 +412,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_sample(args.workload, S, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                                    "cpu": cpu_model()}
+                                    "cpu": cpu_model(), "c_twin": c_twin_sample(args.workload, S)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -964,6 +964,17 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
   BGR_TRY(ensure_pipeline(track->device));
   BGR_TRY(ensure_events(track->device));
 
+  // If anything below fails half way, the internal streams may still be working on the scratch buffers that
+  // `sc` releases when this function returns: drain them first.
+  struct Drain {
+    bool armed = true;
+    ~Drain() {
+      if (armed) {
+        cudaStreamSynchronize(g_pipe.s[0]);
+        cudaStreamSynchronize(g_pipe.s[1]);
+      }
+    }
+  } drain;
   // everything queued on the caller's stream so far (scratch allocation, memset) happens before the chunks
   BGR_CUDA(cudaEventRecord(g_pipe.ready, stream));
   BGR_CUDA(cudaStreamWaitEvent(g_pipe.s[0], g_pipe.ready, 0));
@@ -1006,6 +1017,7 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
     BGR_CUDA(cudaMemcpyAsync(h_aggregate, d_agg, BGR_N_AGG * sizeof(double), cudaMemcpyDeviceToHost, stream));
   }
   BGR_CUDA(cudaStreamSynchronize(stream));
+  drain.armed = false;   // the caller's stream waited on both internal streams and has been synchronised
   return BGR_OK;
 }
 
