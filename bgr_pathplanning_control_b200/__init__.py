@@ -11,7 +11,7 @@ from . import _abi, tracks, sweeps, sharding, roofline          # noqa: F401
 from .vehicle_config import Vehicle_config, conf               # noqa: F401
 from .engine import (Track, RolloutConfig, RolloutResult, MpcConfig, MpcResult, rollout, mpc_evaluate,   # noqa: F401
                      default_params, initial_states, candidate_bank, lqg_design, fp32_peak_probe,
-                     last_kernel_ms, launch_count)
+                     last_kernel_ms, launch_count, identify_dynamics)
 from .controllers import (PurePursuitController, StanleyController, ShadowedStanleyController, AccelerationPIDController,            # noqa: F401
                           LQGAccelerationController, MPCController, get_steering_controller,
                           normalize_angle, find_target_point, compute_control_commands)

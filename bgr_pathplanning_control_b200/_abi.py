@@ -52,11 +52,12 @@ N_CMD = 4
 N_CTRL = 8
 O_STEER, O_ACCEL, O_V_DESIRED, O_KAPPA, O_E_CT, O_THETA_E, O_NEAREST_IND = range(7)
 N_OUT = 8
+SYSID_COLS = 9
 
 EXPORTS = (
     "bgr_abi_version", "bgr_last_error_string", "bgr_device_count", "bgr_track_create", "bgr_track_destroy",
     "bgr_track_info", "bgr_track_tables", "bgr_rollout", "bgr_rollout_host", "bgr_step_host", "bgr_lqg_design",
-    "bgr_mpc_eval", "bgr_mpc_eval_host", "bgr_fp32_peak_probe", "bgr_last_kernel_ms", "bgr_launch_count",
+    "bgr_mpc_eval", "bgr_mpc_eval_host", "bgr_identify_dynamics", "bgr_identify_dynamics_host", "bgr_fp32_peak_probe", "bgr_last_kernel_ms", "bgr_launch_count",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -143,6 +144,10 @@ def load():
     lib.bgr_mpc_eval.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.bgr_mpc_eval_host.restype = C.c_int
     lib.bgr_mpc_eval_host.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.bgr_identify_dynamics.restype = C.c_int
+    lib.bgr_identify_dynamics.argtypes = [i64, i32, vp, vp, vp, vp, vp]
+    lib.bgr_identify_dynamics_host.restype = C.c_int
+    lib.bgr_identify_dynamics_host.argtypes = [i64, i32, vp, vp, vp, vp, vp]
     lib.bgr_fp32_peak_probe.restype = C.c_int
     lib.bgr_fp32_peak_probe.argtypes = [C.c_int, _dp, _dp]
     lib.bgr_last_kernel_ms.restype = C.c_int

@@ -1242,6 +1242,55 @@ extern "C" int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* 
 }
 
 // ================================================================================================
+// batched system identification
+// ================================================================================================
+extern "C" int bgr_identify_dynamics(int64_t n_episodes, int32_t max_rows, const double* d_traj, const int32_t* d_rows,
+                                     double* d_AB, int32_t* d_ok, void* stream_) {
+  if (n_episodes < 0 || max_rows < 2 || n_episodes > 0x7fffffffLL) {
+    set_error("bgr_identify_dynamics: need 0 <= n_episodes < 2^31 and max_rows >= 2");
+    return BGR_ERR_BAD_ARG;
+  }
+  if (n_episodes == 0) return BGR_OK;
+  if (d_traj == nullptr || d_rows == nullptr || d_AB == nullptr || d_ok == nullptr) {
+    set_error("bgr_identify_dynamics: NULL buffer");
+    return BGR_ERR_BAD_ARG;
+  }
+  BGR_CUDA(launch_sysid(d_traj, d_rows, max_rows, n_episodes, d_AB, d_ok, static_cast<cudaStream_t>(stream_)));
+  count_launch();
+  return BGR_OK;
+}
+
+extern "C" int bgr_identify_dynamics_host(int64_t n_episodes, int32_t max_rows, const double* h_traj,
+                                          const int32_t* h_rows, double* h_AB, int32_t* h_ok, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_episodes < 0 || max_rows < 2) {
+    set_error("bgr_identify_dynamics_host: need n_episodes >= 0 and max_rows >= 2");
+    return BGR_ERR_BAD_ARG;
+  }
+  if (n_episodes == 0) return BGR_OK;
+  if (h_traj == nullptr || h_rows == nullptr || h_AB == nullptr || h_ok == nullptr) {
+    set_error("bgr_identify_dynamics_host: NULL buffer");
+    return BGR_ERR_BAD_ARG;
+  }
+  Scratch sc(stream);
+  const size_t E = static_cast<size_t>(n_episodes);
+  const size_t n_traj = E * static_cast<size_t>(max_rows) * BGR_N_TRAJ;
+  double *d_traj, *d_AB;
+  int32_t *d_rows, *d_ok;
+  BGR_TRY(sc.get(&d_traj, n_traj));
+  BGR_TRY(sc.get(&d_rows, E));
+  BGR_TRY(sc.get(&d_AB, E * 6 * BGR_SYSID_COLS));
+  BGR_TRY(sc.get(&d_ok, E));
+  BGR_CUDA(cudaMemcpyAsync(d_traj, h_traj, n_traj * sizeof(double), cudaMemcpyHostToDevice, stream));
+  BGR_CUDA(cudaMemcpyAsync(d_rows, h_rows, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  BGR_TRY(bgr_identify_dynamics(n_episodes, max_rows, d_traj, d_rows, d_AB, d_ok, stream));
+  BGR_CUDA(cudaMemcpyAsync(h_AB, d_AB, E * 6 * BGR_SYSID_COLS * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  BGR_CUDA(cudaMemcpyAsync(h_ok, d_ok, E * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  BGR_CUDA(cudaStreamSynchronize(stream));
+  return BGR_OK;
+}
+
+// ================================================================================================
 // FP32 peak probe
 // ================================================================================================
 extern "C" int bgr_fp32_peak_probe(int device, double* out_tflops, double* out_ginst_per_s) {

@@ -66,6 +66,10 @@ cudaError_t launch_mpc_finalize(const unsigned long long* packed, const float* b
                                 float max_accel, float max_decel, float max_steer, float* best_u, float* best_cost,
                                 int32_t* best_idx, cudaStream_t stream);
 
+// ---- batched system identification (bgr_sysid.cu) ----
+cudaError_t launch_sysid(const double* traj, const int32_t* rows, int max_rows, long long n_episodes, double* AB,
+                         int32_t* ok, cudaStream_t stream);
+
 // ---- small kernels (bgr_misc.cu) ----
 cudaError_t launch_reduce_partials(const double* partials, int n_blocks, double* out, cudaStream_t stream);
 cudaError_t launch_fp32_probe(float* out, int grid, int iters, cudaStream_t stream);

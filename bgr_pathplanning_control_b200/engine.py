@@ -412,3 +412,36 @@ def mpc_evaluate(track, config, state, ref_start, bank, ref_len=None, *, return_
                                K, _ptr(u), _ptr(cost), _ptr(idx), _ptr(costs), stream))
     ms = last_kernel_ms() if time_kernel and E > 0 else None
     return MpcResult(u, cost, idx, costs, ms)
+
+
+def identify_dynamics(traj, rows=None):
+    """Batched ``identify_dynamics`` (old/test_runs_system_id.py:84-111): for every episode of a trajectory dump
+    ``traj`` (E, S, 12) -- or a ``RolloutResult`` run with ``traj=True`` -- the least-squares fit
+    ``x[k+1] = A x[k] + B u[k] + c`` over its logged rows.  Returns ``(A (E, 6, 6), B (E, 6, 2), c (E, 6), ok (E,))``;
+    ``ok`` is False (and the row NaN) where the log is rank deficient.  C = I and D = 0 as in the reference (:106-107).
+    CUDA tensors (zero copy, asynchronous) or numpy arrays (host entry point)."""
+    lib = abi.load()
+    if hasattr(traj, "traj") and hasattr(traj, "status"):
+        res = traj
+        if res.traj is None:
+            raise ValueError("rollout was run without traj=True")
+        traj, rows = res.traj, res.status[:, abi.S_STEPS]
+    if isinstance(traj, np.ndarray):
+        traj = _np(traj, np.float64)
+        E, S = traj.shape[0], traj.shape[1]
+        traj = _np(traj, np.float64, (E, S, abi.N_TRAJ))
+        rows = np.full(E, S, np.int32) if rows is None else _np(rows, np.int32, (E,))
+        AB = np.empty((E, 6, abi.SYSID_COLS))
+        ok = np.empty(E, np.int32)
+        abi.check(lib.bgr_identify_dynamics_host(E, S, _ptr(traj), _ptr(rows), _ptr(AB), _ptr(ok), None))
+        return AB[:, :, :6], AB[:, :, 6:8], AB[:, :, 8], ok.astype(bool)
+    torch = _torch()
+    E, S = int(traj.shape[0]), int(traj.shape[1])
+    if not traj.is_cuda or traj.dtype != torch.float64 or tuple(traj.shape) != (E, S, abi.N_TRAJ) or not traj.is_contiguous():
+        raise ValueError("traj must be a contiguous float64 CUDA tensor of shape (E, S, 12)")
+    rows = torch.full((E,), S, dtype=torch.int32, device=traj.device) if rows is None else rows.to(torch.int32).contiguous()
+    AB = torch.empty((E, 6, abi.SYSID_COLS), dtype=torch.float64, device=traj.device)
+    ok = torch.empty(E, dtype=torch.int32, device=traj.device)
+    stream = torch.cuda.current_stream(traj.device).cuda_stream
+    abi.check(lib.bgr_identify_dynamics(E, S, _ptr(traj), _ptr(rows), _ptr(AB), _ptr(ok), stream))
+    return AB[:, :, :6], AB[:, :, 6:8], AB[:, :, 8], ok.bool()

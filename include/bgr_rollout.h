@@ -309,6 +309,20 @@ int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_
                       const float* h_bank, int32_t n_candidates, float* h_best_u, float* h_best_cost,
                       int32_t* h_best_idx, float* h_costs, void* stream);
 
+/* ---- batched system identification: identify_dynamics (old/test_runs_system_id.py:84-111) for every episode of a
+ *      trajectory dump: least squares x_{k+1} = A x_k + B u_k + c over the logged rows, x = [x, y, yaw, v, yaw_rate,
+ *      beta], u = [accel, steering] (LinearRegression with an intercept on hstack([X, U]) -> Y).
+ *      AB row r of an episode = [A[r][0..5] | B[r][0..1] | c[r]].  ok = 0 (and NaN) for rank-deficient logs. ---- */
+#define BGR_SYSID_COLS 9
+int bgr_identify_dynamics(int64_t n_episodes, int32_t max_rows,
+                          const double* d_traj,   /* [n_episodes][max_rows][BGR_N_TRAJ] as written by bgr_rollout */
+                          const int32_t* d_rows,  /* [n_episodes] logged rows (BGR_S_STEPS) */
+                          double* d_AB,           /* [n_episodes][6][BGR_SYSID_COLS] */
+                          int32_t* d_ok,          /* [n_episodes] */
+                          void* stream);
+int bgr_identify_dynamics_host(int64_t n_episodes, int32_t max_rows, const double* h_traj, const int32_t* h_rows,
+                               double* h_AB, int32_t* h_ok, void* stream);
+
 /* ---- measurement helpers ---- */
 /* FP32 FMA-chain microbenchmark: the roofline denominator for the step kernels (MEASURED_PEAKS.json has
  * only HBM and bf16).  Returns achieved TFLOP/s (2 flops per FMA) and lane-instructions/s. */

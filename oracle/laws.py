@@ -437,3 +437,27 @@ def lap_metrics(timestamp, lateral_error, heading_error):
         "heading_mean": float(np.mean(hed)), "heading_std": _std(hed),       # :4-5
         "lap_time": float(ts[-1] - ts[0]),                                   # :7-8
     }
+
+
+# --------------------------------------------------------------------------------------
+# old/test_runs_system_id.py:84-111  identify_dynamics: LinearRegression (with intercept) of the next
+# state on hstack([state, input]) -- restated on arrays instead of a CSV file.  The reference logs
+# [x, y, yaw, v, yaw_rate, beta, throttle, steering]; here the inputs are the logged (accel, steering).
+# --------------------------------------------------------------------------------------
+def identify_dynamics(states, inputs):
+    """states (T, 6), inputs (T, 2) -> (A (6, 6), B (6, 2), intercept (6,), C, D) as the reference returns them."""
+    from sklearn.linear_model import LinearRegression
+
+    states = np.asarray(states, dtype=np.float64)
+    inputs = np.asarray(inputs, dtype=np.float64)
+    X = states[:-1]                                                   # :97
+    U = inputs[:-1]                                                   # :98
+    Y = states[1:]                                                    # :99
+    reg = LinearRegression()                                          # :101
+    reg.fit(np.hstack([X, U]), Y)                                     # :102
+    AB = reg.coef_                                                    # :103
+    A = AB[:, :X.shape[1]]                                            # :104
+    B = AB[:, X.shape[1]:]                                            # :105
+    C = np.eye(states.shape[1])                                       # :106
+    D = np.zeros((states.shape[1], inputs.shape[1]))                  # :107
+    return A, B, reg.intercept_, C, D
