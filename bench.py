@@ -357,9 +357,14 @@ def run_b200(args):
     w0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    dbg = []
     for i in range(args.steps):
+        td = time.perf_counter()
         r = bgr.rollout(track, cfg, np_params[i % n_sets], np_init[i % n_sets], aggregate=True, out=h_out)
         e2e_steps += float(r.aggregate[abi.A_STEPS])
+        dbg.append((time.perf_counter() - td) * 1e3)
+    if os.environ.get("BGR_BENCH_DEBUG"):
+        print(f"[rank {rank}] e2e ms per step: " + " ".join(f"{x:.1f}" for x in dbg), file=sys.stderr, flush=True)
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
