@@ -238,6 +238,16 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def issue_roofline(ev, sim_steps_per_s, clocks):
+    if not ev:
+        return None
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 4 * mhz * 1e6                                     # warp-instructions per second
+    achieved = sim_steps_per_s / 32.0 * ev["warp_inst_per_warp_step"]
+    return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "warp-inst/s", "frac": achieved / peak,
+            "inst_per_step_source": ev["file"]}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -408,6 +418,10 @@ def run_b200(args):
                 # what ncu measured for this kernel build (one --set full capture per change, profiles/r1_final/):
                 # the kernel is bound by INSTRUCTION ISSUE, not by DRAM (0.08 %) or tensor (0 %)
                 "ncu": NCU_EVIDENCE.get(args.workload),
+                # the roofline that actually binds: warp-instructions issued per second against the issue peak of the
+                # chip (148 SMs x 4 schedulers x 1 instruction per cycle at the SM clock seen under load).  Live steps/s
+                # x the per-step instruction count ncu measured for this build (profiles/r1_final).
+                "issue": issue_roofline(NCU_EVIDENCE.get(args.workload), steps_per_launch / (k_ms * 1e-3), clocks),
                 "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
                         "bytes_per_launch": bytes_launch, "peak_source": peaks_src},
             },
