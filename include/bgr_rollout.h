@@ -12,10 +12,14 @@
  *     across the ABI; bgr_last_error_string() describes the last failure on the calling thread.
  *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensors); pointers named
  *     h_* are HOST pointers.  The library allocates nothing it does not free (stream ordered) before
- *     returning, except the opaque track handle.
+ *     returning, except: the opaque track handle (with the LQG gain tables it caches on first use, freed
+ *     by bgr_track_destroy) and, per calling host thread, two internal streams + a CUDA event pair used
+ *     by the *_host entry points and bgr_last_kernel_ms.
  *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are asynchronous on
  *     that stream unless the name ends in _host (those synchronise the stream before returning).
- *   - handles are immutable after creation; concurrent calls on different streams are allowed.
+ *   - handles are logically immutable after creation (the internal LQG table cache is mutex protected);
+ *     concurrent calls on different streams / host threads are allowed.  A handle must outlive every
+ *     asynchronous call that uses it.
  *   - there is NO CPU fallback anywhere behind this ABI.
  */
 #ifndef BGR_ROLLOUT_H_
