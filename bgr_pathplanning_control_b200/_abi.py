@@ -84,7 +84,7 @@ class RolloutCfg(C.Structure):
                 ("max_steer", C.c_double), ("max_accel", C.c_double), ("max_decel", C.c_double),
                 ("hit_radius", C.c_double), ("tie_eps", C.c_double),
                 ("sigma_xy", C.c_double), ("sigma_yaw", C.c_double), ("sigma_v", C.c_double),
-                ("sigma_cone", C.c_double), ("noise_seed", C.c_uint32), ("reserved1", C.c_uint32),
+                ("sigma_cone", C.c_double), ("noise_seed", C.c_uint32), ("split_steps", C.c_uint32),
                 ("episode_id_base", C.c_int64), ("stanley_max_steer_rate", C.c_double),
                 ("stanley_alpha", C.c_double)]
 

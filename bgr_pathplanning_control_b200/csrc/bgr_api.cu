@@ -728,24 +728,50 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
 }
 
 // Launch the step kernel for `count` episodes whose rows start at the given pointers; `id_offset` is their global
-// position within the call (noise streams are keyed by the global episode id).  `d_partials` points at this
-// range's slice of the per-CTA aggregate partials (ranges start on CTA boundaries, so a chunked call produces the
-// same partials, in the same order, as a single launch).
+// position within the call (noise streams are keyed by the global episode id).  `max_steps` may cap the launch below
+// the configured step count (first phase of a two-phase run); `d_idx` / `d_count` (both or neither) make thread t
+// work on row d_idx[t] for t < *d_count (second phase).
 int launch_range(const Plan& plan, long long id_offset, long long count, const float* d_params, const double* d_init,
-                 float* d_metrics, int32_t* d_status, double* d_traj, double* d_partials, cudaStream_t stream) {
+                 float* d_metrics, int32_t* d_status, double* d_traj, int max_steps, const int32_t* d_idx,
+                 const int32_t* d_count, cudaStream_t stream) {
   RolloutArgs A = plan.A;
   A.params = d_params;
   A.init = d_init;
   A.metrics = d_metrics;
   A.status = d_status;
   A.traj = d_traj;
-  A.block_partials = d_partials;
   A.n_episodes = count;
   A.episode_id_base += id_offset;
+  A.traj_stride = plan.A.max_steps;          // rows of one episode in the trajectory dump
+  A.max_steps = max_steps;
+  A.idx = d_idx;
+  A.count = d_count;
   const int grid = static_cast<int>((count + kRolloutThreads - 1) / kRolloutThreads);
   cudaError_t err = plan.fn(A, grid, plan.smem, stream);
   if (err == cudaSuccess) count_launch();
   return check_cuda(err, "rollout kernel launch");
+}
+
+// One rollout of `count` episodes, in one launch or -- when cfg.split_steps asks for it -- in two phases: a first
+// launch capped at split_steps, then every episode that is still running (status TIMEOUT at the cap) is re-run from
+// scratch to the full step count in a second launch in which the survivors are densely packed.  Episodes are
+// deterministic functions of their own row, so the results are bit-identical to the single launch; what changes is
+// that a warp no longer idles 31 lanes for the one episode in it that runs ten times longer than the rest.
+// `d_work` is scratch for the survivor list: int32[count + 1] (last element = number of survivors).
+int launch_rollout_phases(const Plan& plan, int split_steps, long long id_offset, long long count, const float* d_params,
+                          const double* d_init, float* d_metrics, int32_t* d_status, double* d_traj, int32_t* d_work,
+                          cudaStream_t stream) {
+  const int S = plan.A.max_steps;
+  if (split_steps <= 0 || split_steps >= S || d_work == nullptr)
+    return launch_range(plan, id_offset, count, d_params, d_init, d_metrics, d_status, d_traj, S, nullptr, nullptr, stream);
+  int rc = launch_range(plan, id_offset, count, d_params, d_init, d_metrics, d_status, d_traj, split_steps, nullptr,
+                        nullptr, stream);
+  if (rc != BGR_OK) return rc;
+  int32_t* d_n = d_work + count;
+  BGR_CUDA(cudaMemsetAsync(d_n, 0, sizeof(int32_t), stream));
+  BGR_CUDA(launch_compact_survivors(d_status, count, d_work, d_n, stream));
+  count_launch();
+  return launch_range(plan, id_offset, count, d_params, d_init, d_metrics, d_status, d_traj, S, d_work, d_n, stream);
 }
 
 int check_rollout_buffers(int64_t n_episodes, const void* d_params, const void* d_params64, const void* d_init,
@@ -799,22 +825,30 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   rc = make_plan(track, cfg, sp, d_traj != nullptr, stream, &plan);
   if (rc != BGR_OK) return rc;
   const int grid = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
+  const int split = sp.force_full ? 0 : static_cast<int>(cfg->split_steps);
   double* d_partials = nullptr;
+  int32_t* d_work = nullptr;
   if (d_aggregate != nullptr)
     BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_partials), static_cast<size_t>(grid) * BGR_N_AGG * sizeof(double),
                              stream));
+  if (split > 0 && split < cfg->max_steps)
+    BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_work), static_cast<size_t>(n_episodes + 1) * sizeof(int32_t),
+                             stream));
   rc = ensure_events(track->device);
   if (rc == BGR_OK) rc = check_cuda(cudaEventRecord(g_last.start, stream), "cudaEventRecord");
-  if (rc == BGR_OK) rc = launch_range(plan, 0, n_episodes, d_params, d_init, d_metrics, d_status, d_traj, d_partials, stream);
+  if (rc == BGR_OK)
+    rc = launch_rollout_phases(plan, split, 0, n_episodes, d_params, d_init, d_metrics, d_status, d_traj, d_work, stream);
   if (rc == BGR_OK) {
     rc = check_cuda(cudaEventRecord(g_last.stop, stream), "cudaEventRecord");
     g_last.valid = rc == BGR_OK;
   }
   if (rc == BGR_OK && d_partials != nullptr) {
-    rc = check_cuda(launch_reduce_partials(d_partials, grid, d_aggregate, stream), "aggregate reduction launch");
-    if (rc == BGR_OK) count_launch();
+    rc = check_cuda(launch_aggregate_partials(d_metrics, d_status, n_episodes, d_partials, stream), "aggregate launch");
+    if (rc == BGR_OK) rc = check_cuda(launch_reduce_partials(d_partials, grid, d_aggregate, stream), "aggregate reduction launch");
+    if (rc == BGR_OK) count_launch(2);
   }
   if (d_partials != nullptr) cudaFreeAsync(d_partials, stream);
+  if (d_work != nullptr) cudaFreeAsync(d_work, stream);
   return rc;
 }
 
@@ -958,6 +992,9 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
     BGR_TRY(sc.get(&d_agg, BGR_N_AGG));
     BGR_TRY(sc.get(&d_partials, static_cast<size_t>(grid_total) * BGR_N_AGG));
   }
+  int32_t* d_work = nullptr;   // survivor lists of a two-phase run: one (count + 1)-sized slice per chunk
+  if (cfg->split_steps > 0 && static_cast<int>(cfg->split_steps) < cfg->max_steps)
+    BGR_TRY(sc.get(&d_work, E + static_cast<size_t>(n_episodes / kRolloutThreads) + 64));
   StepPlumbing sp;
   Plan plan;
   BGR_TRY(make_plan(track, cfg, sp, h_traj != nullptr, stream, &plan));
@@ -991,10 +1028,10 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
                              cudaMemcpyHostToDevice, st));
     const bool last = e0 + cnt >= n_episodes;
     if (last) BGR_CUDA(cudaEventRecord(g_last.start, st));
-    BGR_TRY(launch_range(plan, e0, cnt, d_params + o * BGR_N_PARAMS, d_init + o * BGR_N_STATE,
-                         d_metrics + o * BGR_N_METRICS, d_status + o * BGR_N_STATUS,
-                         d_traj != nullptr ? d_traj + o * S * BGR_N_TRAJ : nullptr,
-                         d_partials != nullptr ? d_partials + (o / kRolloutThreads) * BGR_N_AGG : nullptr, st));
+    BGR_TRY(launch_rollout_phases(plan, static_cast<int>(cfg->split_steps), e0, cnt, d_params + o * BGR_N_PARAMS,
+                                  d_init + o * BGR_N_STATE, d_metrics + o * BGR_N_METRICS, d_status + o * BGR_N_STATUS,
+                                  d_traj != nullptr ? d_traj + o * S * BGR_N_TRAJ : nullptr,
+                                  d_work != nullptr ? d_work + o + c : nullptr, st));
     if (last) {
       BGR_CUDA(cudaEventRecord(g_last.stop, st));
       g_last.valid = true;
@@ -1012,8 +1049,9 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
     BGR_CUDA(cudaStreamWaitEvent(stream, g_pipe.done[i], 0));
   }
   if (h_aggregate != nullptr) {
+    BGR_CUDA(launch_aggregate_partials(d_metrics, d_status, n_episodes, d_partials, stream));
     BGR_CUDA(launch_reduce_partials(d_partials, grid_total, d_agg, stream));
-    count_launch();
+    count_launch(2);
     BGR_CUDA(cudaMemcpyAsync(h_aggregate, d_agg, BGR_N_AGG * sizeof(double), cudaMemcpyDeviceToHost, stream));
   }
   BGR_CUDA(cudaStreamSynchronize(stream));

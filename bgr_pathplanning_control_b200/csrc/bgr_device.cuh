@@ -81,10 +81,13 @@ struct RolloutArgs {
   const double* kf_gain;  // [kf_len][2] shared Kalman gain sequence (LQG) or nullptr
   const float2* kf_gain_f; // the same sequence rounded to fp32 (production kernels)
   int32_t kf_len;
-  double* block_partials; // [gridDim.x][BGR_N_AGG] or nullptr
+  // two-phase execution (episodes that outlive the first, short launch are re-run from scratch, densely packed):
+  const int32_t* idx;     // nullptr, or [count] episode row handled by thread t (rows of params / init / outputs)
+  const int32_t* count;   // nullptr (= n_episodes threads are live), or device scalar: number of live threads
   long long n_episodes;
   long long episode_id_base;
   int32_t max_steps;
+  int32_t traj_stride;    // rows per episode in the trajectory dump (the configured step count, also in a capped phase)
   int32_t laps;
   int32_t laps_target;
   int32_t n_total;  // PP: n * laps; Stanley: n
@@ -273,49 +276,6 @@ __device__ __forceinline__ void gaussians4<float>(U4 r, float z[4]) {
   z[1] = -ra * __sinf(ab);
   z[2] = -rc * __cosf(ad);
   z[3] = -rc * __sinf(ad);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Per-CTA partial aggregates (fixed order: lane shuffle tree, then one thread per slot over the warps):
-// deterministic, no atomics.  Reuses the track's shared memory, hence the leading barrier.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_aggregate(const RolloutArgs& A, unsigned char* smem, bool active, int steps,
-                                                int flags, int cone_hits, double lat_mean, double lat_std,
-                                                double lap_time) {
-  if (A.block_partials == nullptr) return;
-  double vals[BGR_N_AGG];
-  const bool finished = active && (flags & (BGR_ST_PATH_END | BGR_ST_LAPS_DONE));
-  vals[BGR_A_EPISODES] = active ? 1.0 : 0.0;
-  vals[BGR_A_STEPS] = static_cast<double>(steps);
-  vals[BGR_A_SUM_LAT_MEAN] = active ? lat_mean : 0.0;
-  vals[BGR_A_SUM_LAT_STD] = (active && steps > 1) ? lat_std : 0.0;
-  vals[BGR_A_SUM_LAP_TIME] = active ? lap_time : 0.0;
-  vals[BGR_A_MIN_LAP_TIME] = finished ? lap_time : 1e300;
-  vals[BGR_A_CONE_HITS] = static_cast<double>(cone_hits);
-  vals[BGR_A_FINISHED] = finished ? 1.0 : 0.0;
-  __syncthreads();  // everyone is done with the track tables: reuse shared memory
-  double* red = reinterpret_cast<double*>(smem);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int a = 0; a < BGR_N_AGG; ++a) {
-    double x = vals[a];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double o = __shfl_down_sync(0xffffffffu, x, off);
-      x = (a == BGR_A_MIN_LAP_TIME) ? fmin(x, o) : x + o;
-    }
-    if (lane == 0) red[warp * BGR_N_AGG + a] = x;
-  }
-  __syncthreads();
-  if (threadIdx.x < BGR_N_AGG) {
-    const int a = threadIdx.x;
-    double x = red[a];
-    for (int w = 1; w < kRolloutThreads / 32; ++w) {
-      const double o = red[w * BGR_N_AGG + a];
-      x = (a == BGR_A_MIN_LAP_TIME) ? fmin(x, o) : x + o;
-    }
-    A.block_partials[static_cast<size_t>(blockIdx.x) * BGR_N_AGG + a] = x;
-  }
 }
 
 constexpr uint32_t kStreamObs = 0;

@@ -72,6 +72,10 @@ cudaError_t launch_sysid(const double* traj, const int32_t* rows, int max_rows, 
 
 // ---- small kernels (bgr_misc.cu) ----
 cudaError_t launch_reduce_partials(const double* partials, int n_blocks, double* out, cudaStream_t stream);
+cudaError_t launch_aggregate_partials(const float* metrics, const int32_t* status, long long n_episodes,
+                                      double* partials, cudaStream_t stream);
+cudaError_t launch_compact_survivors(const int32_t* status, long long n_episodes, int32_t* idx, int32_t* count,
+                                     cudaStream_t stream);
 cudaError_t launch_fp32_probe(float* out, int grid, int iters, cudaStream_t stream);
 
 }  // namespace bgr

@@ -23,6 +23,85 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
   if (lane == 0) out[a] = x;
 }
 
+// Per-256-episode partial aggregates from the per-episode OUTPUT rows (fixed order: lane shuffle tree, then one
+// thread per slot over the warps): deterministic, no atomics, and independent of how the rollout was launched
+// (single launch, pipelined chunks, two-phase).
+__global__ void __launch_bounds__(256) aggregate_partials_kernel(const float* __restrict__ metrics,
+                                                                 const int32_t* __restrict__ status, long long n_episodes,
+                                                                 double* __restrict__ partials) {
+  __shared__ double red[8 * BGR_N_AGG];
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool active = e < n_episodes;
+  double vals[BGR_N_AGG];
+  int steps = 0, flags = 0, hits = 0;
+  float lat_mean = 0.f, lat_std = 0.f, lap_time = 0.f;
+  if (active) {
+    const float* mrow = metrics + e * BGR_N_METRICS;
+    const int32_t* srow = status + e * BGR_N_STATUS;
+    lat_mean = mrow[BGR_M_LAT_MEAN]; lat_std = mrow[BGR_M_LAT_STD]; lap_time = mrow[BGR_M_LAP_TIME];
+    flags = srow[BGR_S_FLAGS]; steps = srow[BGR_S_STEPS]; hits = srow[BGR_S_CONE_HITS];
+  }
+  const bool finished = active && (flags & (BGR_ST_PATH_END | BGR_ST_LAPS_DONE));
+  vals[BGR_A_EPISODES] = active ? 1.0 : 0.0;
+  vals[BGR_A_STEPS] = static_cast<double>(steps);
+  vals[BGR_A_SUM_LAT_MEAN] = active ? static_cast<double>(lat_mean) : 0.0;
+  vals[BGR_A_SUM_LAT_STD] = (active && steps > 1) ? static_cast<double>(lat_std) : 0.0;
+  vals[BGR_A_SUM_LAP_TIME] = active ? static_cast<double>(lap_time) : 0.0;
+  vals[BGR_A_MIN_LAP_TIME] = finished ? static_cast<double>(lap_time) : 1e300;
+  vals[BGR_A_CONE_HITS] = static_cast<double>(hits);
+  vals[BGR_A_FINISHED] = finished ? 1.0 : 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < BGR_N_AGG; ++a) {
+    double x = vals[a];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double o = __shfl_down_sync(0xffffffffu, x, off);
+      x = (a == BGR_A_MIN_LAP_TIME) ? fmin(x, o) : x + o;
+    }
+    if (lane == 0) red[warp * BGR_N_AGG + a] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < BGR_N_AGG) {
+    const int a = threadIdx.x;
+    double x = red[a];
+    for (int w = 1; w < 8; ++w) {
+      const double o = red[w * BGR_N_AGG + a];
+      x = (a == BGR_A_MIN_LAP_TIME) ? fmin(x, o) : x + o;
+    }
+    partials[static_cast<size_t>(blockIdx.x) * BGR_N_AGG + a] = x;
+  }
+}
+
+cudaError_t launch_aggregate_partials(const float* metrics, const int32_t* status, long long n_episodes,
+                                      double* partials, cudaStream_t stream) {
+  const unsigned grid = static_cast<unsigned>((n_episodes + 255) / 256);
+  aggregate_partials_kernel<<<grid, 256, 0, stream>>>(metrics, status, n_episodes, partials);
+  return cudaGetLastError();
+}
+
+// Survivors of a capped first phase (status TIMEOUT with steps == cap): their rows, densely packed (order is
+// whatever the atomics give -- results do not depend on it), and their number.
+__global__ void __launch_bounds__(256) compact_survivors_kernel(const int32_t* __restrict__ status, long long n_episodes,
+                                                                int32_t* __restrict__ idx, int32_t* __restrict__ count) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool alive = e < n_episodes && status[e * BGR_N_STATUS + BGR_S_FLAGS] == BGR_ST_TIMEOUT;
+  const unsigned mask = __ballot_sync(0xffffffffu, alive);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(mask) - 1) base = atomicAdd(count, __popc(mask));
+  base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+  if (alive) idx[base + __popc(mask & ((1u << lane) - 1u))] = static_cast<int32_t>(e);
+}
+
+cudaError_t launch_compact_survivors(const int32_t* status, long long n_episodes, int32_t* idx, int32_t* count,
+                                     cudaStream_t stream) {
+  const unsigned grid = static_cast<unsigned>((n_episodes + 255) / 256);
+  compact_survivors_kernel<<<grid, 256, 0, stream>>>(status, n_episodes, idx, count);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_reduce_partials(const double* partials, int n_blocks, double* out, cudaStream_t stream) {
   reduce_partials_kernel<<<1, 32 * BGR_N_AGG, 0, stream>>>(partials, n_blocks, out);
   return cudaGetLastError();

@@ -47,9 +47,11 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
     tma_bulk_g2s(s_guard2, A.trk.guard2, b_g, bar);
   }
 
-  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool active = e < A.n_episodes;
-  const long long er = active ? e : 0;
+  const long long t_glob = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool active = t_glob < (A.count != nullptr ? static_cast<long long>(__ldg(A.count)) : A.n_episodes);
+  // row of this thread's episode: identity, or through the survivor list of a two-phase run
+  const long long e = active ? (A.idx != nullptr ? static_cast<long long>(__ldg(A.idx + t_glob)) : t_glob) : 0;
+  const long long er = e;
 
   // ---- per-episode parameters: four coalesced 128-bit loads of the 64 B row ----
   Real Lf, kp, ki, kd, tspeed, k_expo, k_st, k_soft, mu, c_f, c_r, mass, I_z;
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
           if (first_tie < 0) first_tie = k;
         }
         if (A.traj != nullptr) {
-          double* row = A.traj + (static_cast<size_t>(e) * A.max_steps + k) * BGR_N_TRAJ;
+          double* row = A.traj + (static_cast<size_t>(e) * A.traj_stride + k) * BGR_N_TRAJ;
           row[BGR_T_X] = X; row[BGR_T_Y] = Y; row[BGR_T_YAW] = YAW; row[BGR_T_V] = V;
           row[BGR_T_R] = r; row[BGR_T_BETA] = beta; row[BGR_T_STEER] = delta; row[BGR_T_ACCEL] = acc;
           row[BGR_T_TARGET_IND] = ti; row[BGR_T_NEAREST_IND] = j_true;
@@ -577,7 +579,6 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
     }
   }
 
-  block_aggregate(A, smem, active, steps, flags, cone_hits, lat_mean, lat_std, lap_time);
 }
 
 // Host-side launcher, one explicit specialisation per (Real, STEER, ACCEL, MODEL, EXTRAS).

@@ -130,6 +130,7 @@ class RolloutConfig:
     sigma_cone: float = 0.0
     noise_seed: int = 0
     episode_id_base: int = 0
+    split_steps: int = 0             # > 0: two-phase execution (short first launch, survivors re-run packed)
     stanley_shadowed: bool = False   # the dead-code Stanley variant (core/controllers.py:234-324); labelled extra
     stanley_max_steer_rate: float = 0.0   # 0 = reference default deg2rad(30) rad/s
     stanley_alpha: float = 0.0            # 0 = reference default 0.5
@@ -148,6 +149,7 @@ class RolloutConfig:
                   "sigma_xy", "sigma_yaw", "sigma_v", "sigma_cone"):
             setattr(c, k, float(getattr(self, k)))
         c.noise_seed = int(self.noise_seed) & 0xFFFFFFFF
+        c.split_steps = max(0, int(self.split_steps))
         c.episode_id_base = int(self.episode_id_base)
         return c
 

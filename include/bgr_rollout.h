@@ -191,7 +191,9 @@ typedef struct bgr_rollout_cfg {
   /* observation noise (config 5); all sigmas 0 = off.  Philox4x32-10, key = (seed, episode id) */
   double sigma_xy, sigma_yaw, sigma_v, sigma_cone;
   uint32_t noise_seed;
-  uint32_t reserved1;
+  uint32_t split_steps;    /* 0 = one launch.  > 0: two-phase execution -- a first launch capped at split_steps, then the
+                              episodes still running are re-run from scratch, densely packed, to max_steps.  Results
+                              are bit-identical; pays off when most episodes end early (laps_target, open paths) */
   int64_t episode_id_base; /* global id of episode 0 of this call (multi-GPU shards) */
   /* BGR_CFG_STANLEY_SHADOWED only (core/controllers.py:234): 0 = the reference defaults deg2rad(30) rad/s and 0.5 */
   double stanley_max_steer_rate;

@@ -80,7 +80,7 @@ def test_struct_layouts_match_a_c_compiler(tmp_path):
         "bgr_track_info_t": (abi.TrackInfo, ["n", "device", "smem_bytes_fp32", "guard_min", "ds_max", "rival_total",
                                                "rival_max", "rival_unlisted"]),
         "bgr_rollout_cfg_t": (abi.RolloutCfg, ["steer_kind", "max_steps", "flags", "dt", "hit_radius", "tie_eps",
-                                                "sigma_cone", "noise_seed", "episode_id_base",
+                                                "sigma_cone", "noise_seed", "split_steps", "episode_id_base",
                                                 "stanley_max_steer_rate", "stanley_alpha"]),
         "bgr_mpc_cfg_t": (abi.MpcCfg, ["horizon", "dt", "target_speed", "q", "r", "max_steer", "flags"]),
     }

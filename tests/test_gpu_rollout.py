@@ -380,3 +380,33 @@ def test_long_track_stages_only_the_xy_table(cuda_device):
         cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=600, laps=2)
         init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.3, 0.3, E), v0=5.0)
         compare(ta, track, cfg, params, init, range(0, E, 2))
+
+
+@pytest.mark.parametrize("split", [1, 37, 256, 5000])
+def test_two_phase_execution_is_bit_identical(oval, cuda_device, split):
+    """cfg.split_steps: a first launch capped at split_steps, then the episodes still running are re-run from
+    scratch, densely packed.  Scheduling only -- every output row must be bit-identical to the single launch, on the
+    device path, on the pipelined host path, with early termination, noise (keyed by the global episode id), cones
+    and a trajectory dump."""
+    import torch
+    ta, track = oval
+    E = 3000
+    params = bgr.sweeps.pp_sweep_params(E, start=32 * 16384 + 99)
+    params[:, abi.P_TARGET_SPEED] = np.linspace(3.0, 9.0, E)           # lap times spread over a factor of three
+    init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.3, 0.3, E))
+    kw = dict(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=900, laps=2, laps_target=1,
+              sigma_xy=0.02, sigma_v=0.05, noise_seed=11, hit_radius=0.6, episode_id_base=777)
+    one = bgr.rollout(track, bgr.RolloutConfig(**kw), params, init, aggregate=True)
+    two = bgr.rollout(track, bgr.RolloutConfig(split_steps=split, **kw), params, init, aggregate=True)      # host path
+    assert np.array_equal(one.metrics, two.metrics, equal_nan=True) and np.array_equal(one.status, two.status)
+    assert np.array_equal(one.aggregate, two.aggregate)
+    dev = bgr.rollout(track, bgr.RolloutConfig(split_steps=split, **kw), torch.from_numpy(params).to(cuda_device),
+                      torch.from_numpy(init).to(cuda_device), aggregate=True, traj=(split == 37))
+    assert np.array_equal(one.metrics, dev.metrics.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(one.status, dev.status.cpu().numpy())
+    assert np.array_equal(one.aggregate, dev.aggregate.cpu().numpy())
+    fin = (one.status[:, abi.S_FLAGS] & abi.ST_LAPS_DONE) != 0
+    assert 0.2 < fin.mean() < 1.0, "the sweep must mix finished and timed-out episodes"
+    if split == 37:
+        ref = bgr.rollout(track, bgr.RolloutConfig(**kw), params[:64], init[:64], traj=True)
+        assert np.array_equal(ref.traj, dev.traj.cpu().numpy()[:64])
