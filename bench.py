@@ -458,10 +458,9 @@ def run_skidpad_mc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, bar
     jobs = []
     for g, (steer, accel, model) in enumerate(kinds):
         lo = (rank * len(kinds) + g) * per
-        # two-phase execution: most episodes of this Monte Carlo end long before the step cap (pure pursuit reaches
-        # the path end after ~950 steps, the Stanley kinds lock onto the exit straight after ~130), a few run to the cap
-        split = int(os.environ.get("BGR_MC_SPLIT", "-1"))
-        split = (1024 if steer == "pure_pursuit" else 192) if split < 0 else split
+        # (two-phase execution, cfg.split_steps, does not pay here: measured, the kernel time of the Stanley kinds is the
+        # serial latency of their few 1 500-step episodes, ~5.6 us per step for a lone warp, packed or not)
+        split = max(0, int(os.environ.get("BGR_MC_SPLIT", "0")))
         cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=1, episode_id_base=lo,
                                 split_steps=split, **noise)
         init = bgr.initial_states(ta, per, index=0, v0=5.0 if model == "dynamic" else 0.0)
