@@ -176,12 +176,11 @@ __device__ __forceinline__ float normalize_angle(float a) {
   const float kPiF = 3.14159274101257324f;       // float(pi)
   const float kTwoPiHi = 6.28318548202514648f;   // float(2 pi)
   const float kTwoPiLo = -1.74845553146951715e-7f;  // 2 pi - float(2 pi)
-  if (a >= kPiF) {
-    a = (a - kTwoPiHi) - kTwoPiLo;
-  } else if (a < -kPiF) {
-    a = (a + kTwoPiHi) + kTwoPiLo;
-  }
-  return a;
+  // k = +1 above pi, -1 below -pi, else 0; the two fused steps round exactly like (a -+ hi) -+ lo and leave a
+  // untouched for k = 0 (five instructions, no branch)
+  const float k = (a >= kPiF ? 1.0f : 0.0f) - (a < -kPiF ? 1.0f : 0.0f);
+  a = fmaf(k, -kTwoPiHi, a);
+  return fmaf(k, -kTwoPiLo, a);
 }
 
 // Heading handed to the laws.  double: the unwrapped yaw itself (reference semantics).  float: yaw
