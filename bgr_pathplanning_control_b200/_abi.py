@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libbgr_rollout.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "bgr_rollout.h")
 
 # ---- constants restated from include/bgr_rollout.h (tests/test_abi.py checks them against the header) ----
-BGR_ABI_VERSION = 1
+BGR_ABI_VERSION = 2
 BGR_OK, BGR_ERR_BAD_ARG, BGR_ERR_CUDA, BGR_ERR_TOO_LARGE, BGR_ERR_ALLOC, BGR_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 STEER_PURE_PURSUIT, STEER_STANLEY = 0, 1
 ACCEL_PID, ACCEL_LQG = 0, 1
@@ -86,7 +86,9 @@ class RolloutCfg(C.Structure):
                 ("sigma_xy", C.c_double), ("sigma_yaw", C.c_double), ("sigma_v", C.c_double),
                 ("sigma_cone", C.c_double), ("noise_seed", C.c_uint32), ("split_steps", C.c_uint32),
                 ("episode_id_base", C.c_int64), ("stanley_max_steer_rate", C.c_double),
-                ("stanley_alpha", C.c_double)]
+                ("stanley_alpha", C.c_double),
+                ("replan_horizon", C.c_int32), ("replan_stride", C.c_int32), ("replan_after", C.c_int32),
+                ("reserved2", C.c_int32), ("planner_lookahead", C.c_double)]
 
 
 class MpcCfg(C.Structure):

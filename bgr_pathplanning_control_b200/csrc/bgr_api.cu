@@ -575,6 +575,16 @@ int validate_cfg(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const c
               who, cfg->max_steps, cfg->laps, cfg->laps_target, cfg->dt, cfg->wheelbase, cfg->max_steer);
     return BGR_ERR_BAD_ARG;
   }
+  if (cfg->replan_horizon != 0) {
+    if (cfg->steer_kind != BGR_STEER_PURE_PURSUIT || cfg->replan_horizon < 2 || cfg->replan_stride < 0 ||
+        cfg->replan_after < 0 || cfg->planner_lookahead < 0.0 ||
+        static_cast<long long>(cfg->replan_horizon) * (cfg->replan_stride > 0 ? cfg->replan_stride : 1) > 0x3fffffffLL) {
+      set_error("%s: re-planning replay needs pure pursuit, replan_horizon >= 2, replan_stride >= 0, replan_after >= 0 "
+                "(got steer %d, horizon %d, stride %d, after %d)", who, cfg->steer_kind, cfg->replan_horizon,
+                cfg->replan_stride, cfg->replan_after);
+      return BGR_ERR_BAD_ARG;
+    }
+  }
   if (static_cast<long long>(track->n) * cfg->laps > 0x3fffffffLL) {
     set_error("%s: n * laps overflows the target index", who);
     return BGR_ERR_BAD_ARG;
@@ -610,7 +620,9 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   const bool cones_on = cfg->hit_radius > 0.0 && track->n_cones > 0;
   const bool noise_on = cfg->sigma_xy > 0.0 || cfg->sigma_yaw > 0.0 || cfg->sigma_v > 0.0;
   const bool shadowed = (cfg->flags & BGR_CFG_STANLEY_SHADOWED) != 0 && cfg->steer_kind == BGR_STEER_STANLEY;
-  const bool full = f64 || cones_on || noise_on || want_traj || (cfg->flags & BGR_CFG_AUDIT) || sp.force_full || shadowed;
+  const bool replan = cfg->replan_horizon > 0;
+  const bool full = f64 || cones_on || noise_on || want_traj || (cfg->flags & BGR_CFG_AUDIT) || sp.force_full ||
+                    shadowed || replan;
 
   plan->smem = f64 ? rollout_smem_bytes<double>(track->n_pad) : rollout_smem_bytes<float>(track->n_pad);
   bool attr_in_smem = true;
@@ -625,6 +637,10 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
     return BGR_ERR_TOO_LARGE;
   }
 
+  if (replan && sp.ctrl_in != nullptr) {
+    set_error("bgr_step_host: re-planning replay is a rollout mode (the planner's path and index are episode state)");
+    return BGR_ERR_BAD_ARG;
+  }
   RolloutArgs& A = plan->A;
   std::memset(&A, 0, sizeof(A));
   A.trk = track->view();
@@ -670,6 +686,11 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   A.st_alpha = cfg->stanley_alpha > 0.0 ? cfg->stanley_alpha : 0.5;
   A.f.st_max_delta = static_cast<float>(A.st_rate * cfg->dt);
   A.f.st_alpha = static_cast<float>(A.st_alpha);
+  A.replan_M = replan ? cfg->replan_horizon : 0;
+  A.replan_q = cfg->replan_stride > 0 ? cfg->replan_stride : 1;
+  A.replan_after = cfg->replan_after;
+  A.plan_Lf = cfg->planner_lookahead > 0.0 ? cfg->planner_lookahead : 5.5;
+  A.f.plan_Lf = static_cast<float>(A.plan_Lf);
   A.seed = cfg->noise_seed;
   A.cones_on = cones_on ? 1 : 0;
   A.attr_in_smem = attr_in_smem ? 1 : 0;

@@ -68,6 +68,7 @@ struct RolloutF32 {
   float dt, inv_dt, WB, inv_WB, l_f, l_r, max_steer, tan_max_steer, max_accel, max_decel;
   float tie_eps, hit_radius, K0, K1, sigma_xy, sigma_yaw, sigma_v, sigma_cone;
   float st_max_delta, st_alpha;   // shadowed Stanley: max_steer_rate * dt, alpha
+  float plan_Lf;                  // re-planning replay: the planner's own look-ahead distance
 };
 
 struct RolloutArgs {
@@ -98,6 +99,9 @@ struct RolloutArgs {
   double sigma_xy, sigma_yaw, sigma_v, sigma_cone;
   double st_rate, st_alpha;   // shadowed Stanley variant (core/controllers.py:234-324)
   int32_t stanley_shadowed;
+  // receding-horizon re-planning replay (nodes/planner.py:26,62,72-77); replan_M = 0: off
+  int32_t replan_M, replan_q, replan_after;
+  double plan_Lf;
   uint32_t seed;
   int32_t cones_on;
   int32_t attr_in_smem;   // fp32 kernels: attr / guard tables staged in shared memory (short tracks) or read via L1

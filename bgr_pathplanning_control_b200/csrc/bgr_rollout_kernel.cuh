@@ -105,6 +105,9 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
   double s_lat = 0, s_lat2 = 0, s_head = 0, s_head2 = 0;
   Real max_lat = 0;
   int steps = 0, flags = 0, ti = 0, tim = 0, near = -1, lap = 0;
+  // re-planning replay (nodes/planner.py): first waypoint of the current local path, the planner's own index on it
+  int plan_org = -1, plan_ti = 0;
+  const bool replan = EXTRAS && STEER == BGR_STEER_PURE_PURSUIT && A.replan_M > 0;
   int cone_hits = 0, ties = 0, first_tie = -1, fallbacks = 0;
   uint32_t hitmask[EXTRAS ? BGR_MAX_CONES / 32 : 1];
   if constexpr (EXTRAS) {
@@ -288,15 +291,47 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
       if (!steer_on) {
         delta = static_cast<Real>(A.cmd[er * BGR_N_CMD + BGR_CMD_STEER]);
       } else if constexpr (STEER == BGR_STEER_PURE_PURSUIT) {
+        if (replan) {
+          // receding-horizon replay: Planner.update (nodes/planner.py:26-77), then compute_steering on the LOCAL path
+          // (nodes/controller.py:56-61); local point k is waypoint plan_org + k * replan_q of the centreline
+          if (plan_org < 0 || plan_ti > A.replan_after) {            // :26
+            plan_org = nearest(oxl, oyl, near);                      // the new path starts at the car
+            plan_ti = 0;                                             // :62
+          }
+          const int M = A.replan_M, q = A.replan_q;
+          auto waypoint_of = [&](int kk) -> int {
+            const long long g = static_cast<long long>(plan_org) + static_cast<long long>(q) * kk;
+            return closed ? static_cast<int>(g % n) : static_cast<int>(g < n - 1 ? g : n - 1);
+          };
+          const Real pl = static_cast<Real>(A.plan_Lf);
+          const Real pl_metric = kF64 ? pl : pl * pl;
+          const Real tie_pl = kF64 ? tie_eps : tie_eps * (Real(2) * pl + tie_eps);
+          while (plan_ti < M - 1) {                                  // the planner's own scan, :72-77
+            const Real d = dist(waypoint_of(plan_ti), oxl, oyl);
+            tie_now |= fabs(d - pl_metric) <= tie_pl;
+            if (d >= pl_metric) break;
+            ++plan_ti;
+          }
+          int lt = plan_ti;                                          // data["target_ind"], :101
+          while (lt < M) {                                           // core/controllers.py:212-218
+            const Real d = dist(waypoint_of(lt), oxl, oyl);
+            tie_now |= fabs(d - Lf_metric) <= tie_pp;
+            if (d >= Lf_metric) break;
+            ++lt;
+          }
+          if (lt >= M) lt = M - 1;                                   // :219-220
+          ti = lt;
+          tim = waypoint_of(lt);
+        }
         // forward scan for the first index with distance >= Lf (core/controllers.py:212-220)
-        while (ti < n_total) {
+        while (!replan && ti < n_total) {
           const Real d = dist(tim, oxl, oyl);
           if constexpr (EXTRAS) tie_now |= fabs(d - Lf_metric) <= tie_pp;
           if (d >= Lf_metric) break;
           ++ti;
           tim = (tim + 1 == n) ? 0 : tim + 1;
         }
-        if (ti >= n_total) {
+        if (!replan && ti >= n_total) {
           ti = n_total - 1;
           tim = n - 1;
         }
@@ -534,7 +569,8 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
       steps = k + 1;
       if (!(isfinite(X) && isfinite(Y) && isfinite(YAW) && isfinite(V) && isfinite(r) && isfinite(beta)))
         flags |= BGR_ST_NONFINITE;
-      if (STEER == BGR_STEER_PURE_PURSUIT && ti >= n_total - 1) flags |= BGR_ST_PATH_END;
+      if (STEER == BGR_STEER_PURE_PURSUIT && !replan && ti >= n_total - 1) flags |= BGR_ST_PATH_END;
+      if (replan && !closed && tim >= n - 1) flags |= BGR_ST_PATH_END;
       if (STEER == BGR_STEER_STANLEY && !closed && ti >= n_total - 1) flags |= BGR_ST_PATH_END;
       if (A.laps_target > 0 && lap >= A.laps_target) flags |= BGR_ST_LAPS_DONE;
       if (flags) break;

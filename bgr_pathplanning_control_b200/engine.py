@@ -134,6 +134,13 @@ class RolloutConfig:
     stanley_shadowed: bool = False   # the dead-code Stanley variant (core/controllers.py:234-324); labelled extra
     stanley_max_steer_rate: float = 0.0   # 0 = reference default deg2rad(30) rad/s
     stanley_alpha: float = 0.0            # 0 = reference default 0.5
+    # receding-horizon re-planning replay (nodes/planner.py:26,62,72-77; pure pursuit only): the controller sees a
+    # local path of `replan_horizon` points (every `replan_stride`-th centreline waypoint from the one nearest to the
+    # car), re-planned whenever the planner's own look-ahead index has passed `replan_after`.  0 = off.
+    replan_horizon: int = 0
+    replan_stride: int = 1
+    replan_after: int = 3                 # nodes/planner.py:26
+    planner_lookahead: float = conf.LOOKAHEAD_DISTANCE   # nodes/planner.py:75
 
     def to_struct(self):
         c = abi.RolloutCfg()
@@ -151,6 +158,8 @@ class RolloutConfig:
         c.noise_seed = int(self.noise_seed) & 0xFFFFFFFF
         c.split_steps = max(0, int(self.split_steps))
         c.episode_id_base = int(self.episode_id_base)
+        c.replan_horizon, c.replan_stride = int(self.replan_horizon), int(self.replan_stride)
+        c.replan_after, c.planner_lookahead = int(self.replan_after), float(self.planner_lookahead)
         return c
 
 

@@ -34,7 +34,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden: only this ABI is exported */
 #endif
 
-#define BGR_ABI_VERSION 1
+#define BGR_ABI_VERSION 2
 
 /* ---- status codes ---- */
 #define BGR_OK 0
@@ -198,6 +198,20 @@ typedef struct bgr_rollout_cfg {
   /* BGR_CFG_STANLEY_SHADOWED only (core/controllers.py:234): 0 = the reference defaults deg2rad(30) rad/s and 0.5 */
   double stanley_max_steer_rate;
   double stanley_alpha;
+  /* ---- receding-horizon re-planning replay (BGR_STEER_PURE_PURSUIT only; replan_horizon = 0: off) -- the regime the
+   *      live stack actually drives in (nodes/planner.py:26,62,72-77 feeding nodes/controller.py:56-62): the controller
+   *      sees a SHORT local path; the planner keeps its own look-ahead index on it (scan :72-77 with
+   *      conf.LOOKAHEAD_DISTANCE) and plans a new path, index reset to 0 (:62), whenever that index has passed
+   *      replan_after (:26).  fsd-path-planning itself is out of scope: the local path planned from a car pose is the
+   *      WINDOW of the handle's centreline that starts at the waypoint nearest to the (observed) car,
+   *      local point k = waypoint j0 + k * replan_stride (mod n when closed, clipped to n - 1 when open).
+   *      The reported target index (BGR_S_TARGET_IND, BGR_T_TARGET_IND) is the controller's LOCAL index;
+   *      open tracks end (BGR_ST_PATH_END) when the target is the last waypoint; cfg.laps is ignored. */
+  int32_t replan_horizon;   /* M >= 2 points per local path (about 40 live) */
+  int32_t replan_stride;    /* >= 1; 0 = 1 */
+  int32_t replan_after;     /* re-plan when the planner's index > this; reference value 3 (nodes/planner.py:26) */
+  int32_t reserved2;
+  double planner_lookahead; /* the planner's own look-ahead (nodes/planner.py:75); 0 = 5.5 (vehicle_config.py:37) */
 } bgr_rollout_cfg_t;
 
 #define BGR_MPC_EXPLICIT_ROLLOUT 1 /* bgr_mpc_cfg_t.flags: score candidates by the explicit stage-by-stage rollout

@@ -21,6 +21,14 @@ Per step k (t = k * dt), for an episode that has not terminated:
                    lap => lap += 1 (backward => lap -= 1)
   8. vehicle       State.update(a, delta) -> dynamic bicycle (car_state.py:178-223), or the
                    ORACLE-DEFINED kinematic bicycle
+  2'. re-planning  (``replan_horizon`` > 0, pure pursuit only) the regime of the live stack: Planner.update
+                   (nodes/planner.py:17-102) keeps a SHORT local path and its own look-ahead index on it; it plans a
+                   new path (index back to 0, :62) whenever that index has passed ``replan_after`` (:26), advances the
+                   index by its own scan with conf.LOOKAHEAD_DISTANCE (:72-77) and hands path + index to the
+                   controller, which runs compute_steering on the local path from that index (nodes/controller.py:
+                   56-62).  ORACLE-DEFINED stand-in for fsd-path-planning (out of scope): the path planned from a car
+                   position is the window of the centreline starting at the waypoint nearest to it, every
+                   ``replan_stride``-th waypoint, ``replan_horizon`` points (modulo n when closed, clipped when open).
   9. termination   after the step: target index reached the last path index (old/animation_loop.py:71
                    ``lastIndex > target_ind``), or ``laps_target`` laps completed, or non-finite state;
                    else the step cap (``T >= curr_time`` in the legacy loop).
@@ -81,6 +89,9 @@ class RolloutSpec:
     laps_target: int = 0              # stop after this many completed laps (0 = off)
     hit_radius: float = 0.0           # 0 = cone hits off
     noise: NoiseSpec | None = None
+    replan_horizon: int = 0           # > 0: receding-horizon replay with local paths of this many points
+    replan_stride: int = 1
+    replan_after: int = 3             # nodes/planner.py:26
     conf: laws.VehicleConfig = field(default_factory=lambda: laws.CONF)
 
 
@@ -92,6 +103,22 @@ class Track:
     kappa: np.ndarray
     closed: bool = True
     cones: np.ndarray = field(default_factory=lambda: np.zeros((0, 2)))
+
+
+def window_path_indices(n: int, closed: bool, j0: int, horizon: int, stride: int) -> np.ndarray:
+    """ORACLE-DEFINED stand-in for the planner: waypoint indices of the local path planned at waypoint ``j0``."""
+    g = j0 + stride * np.arange(horizon, dtype=np.int64)
+    return g % n if closed else np.minimum(g, n - 1)
+
+
+def planner_scan(cx, cy, x, y, target_ind: int, lookahead: float) -> int:
+    """The planner's own index update, nodes/planner.py:72-77 (note ``< len - 1``, unlike the controller's scan)."""
+    while target_ind < len(cx) - 1:
+        distance = np.hypot(cx[target_ind] - x, cy[target_ind] - y)
+        if distance >= lookahead:
+            break
+        target_ind += 1
+    return target_ind
 
 
 def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode_id: int = 0,
@@ -133,6 +160,11 @@ def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode
         cones = cones + noise.sigma_cone * np.stack([z[0], z[1]], axis=1)
     cone_hit = np.zeros(len(cones), dtype=bool)
 
+    replan = spec.replan_horizon > 0
+    if replan and spec.steer != "pure_pursuit":
+        raise ValueError("re-planning replay is defined for pure pursuit (nodes/controller.py:23)")
+    plan_idx = None                  # Planner.current_path (as waypoint indices), nodes/planner.py:13
+    plan_ti = 0                      # Planner.target_ind, :14
     ti = 0
     prev_steer = 0.0                 # StanleyController.previous_steering (:250), shadowed variant only
     prev_near = None
@@ -154,7 +186,30 @@ def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode
             ov = v + noise.sigma_v * float(z[3])
         # 2. steering
         pp_margin = math.inf
-        if spec.steer == "pure_pursuit":
+        if replan:
+            if plan_idx is None or plan_ti > spec.replan_after:                         # nodes/planner.py:26
+                d_obs = np.hypot(cx_lap - ox, cy_lap - oy)
+                j0 = int(np.argmin(d_obs))
+                if record:           # decision margin of the planner's start point (near-tie recognition in the tests)
+                    part = np.partition(d_obs, 1)
+                    pp_margin = min(pp_margin, float(part[1] - part[0]))
+                plan_idx = window_path_indices(n_lap, track.closed, j0, spec.replan_horizon, spec.replan_stride)
+                plan_ti = 0                                                             # :62
+            lx, ly = cx_lap[plan_idx], cy_lap[plan_idx]
+            plan_ti = planner_scan(lx, ly, ox, oy, plan_ti, conf.LOOKAHEAD_DISTANCE)    # :72-77
+            if record:
+                for i in range(plan_ti + 1):      # (margins of both scans; the planner's own tests first)
+                    pp_margin = min(pp_margin, abs(float(np.hypot(lx[i] - ox, ly[i] - oy)) - conf.LOOKAHEAD_DISTANCE))
+                i = plan_ti
+                while i < len(lx):
+                    d = float(np.hypot(lx[i] - ox, ly[i] - oy))
+                    pp_margin = min(pp_margin, abs(d - p[P_LF]))
+                    if d >= p[P_LF]:
+                        break
+                    i += 1
+            delta, ti = laws.pure_pursuit_steering(ox, oy, oyaw, lx, ly, plan_ti, p[P_LF],   # nodes/controller.py:61
+                                                   conf.WB, conf.MAX_STEER)
+        elif spec.steer == "pure_pursuit":
             if record:
                 i = ti
                 while i < n_tot:
@@ -175,7 +230,11 @@ def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode
         else:
             raise ValueError(spec.steer)
         # 3. curvature lookup (nodes/controller.py:62)
-        kappa = curve_tot[ti] if ti < len(curve_tot) else curve_tot[-1]
+        if replan:
+            curve_loc = curve_lap[plan_idx]
+            kappa = curve_loc[ti] if ti < len(curve_loc) else curve_loc[-1]
+        else:
+            kappa = curve_tot[ti] if ti < len(curve_tot) else curve_tot[-1]
         # 4. acceleration
         if spec.accel == "pid":
             a, _ = laws.pid_acceleration(pid, ov, kappa, p[P_KP], p[P_KI], p[P_KD], dt,
@@ -223,7 +282,10 @@ def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode
         # 9. termination
         if not all(math.isfinite(s) for s in state):
             status |= ST_NONFINITE
-        if spec.steer == "pure_pursuit" and ti >= n_tot - 1:
+        if replan:
+            if not track.closed and plan_idx[ti] >= n_lap - 1:      # the target is the last waypoint of an open path
+                status |= ST_PATH_END
+        elif spec.steer == "pure_pursuit" and ti >= n_tot - 1:
             status |= ST_PATH_END
         if spec.steer in ("stanley", "stanley_shadowed") and not track.closed and ti >= n_tot - 1:
             status |= ST_PATH_END

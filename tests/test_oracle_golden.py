@@ -259,3 +259,35 @@ def test_shadowed_stanley_variant():
     assert_same(out["traj"], want, "traj")
     assert_same(out["steer"], unhex(L["steer"]), "steer")
     assert_same(out["accel"], unhex(L["accel"]), "accel")
+
+
+@pytest.mark.parametrize("name", ["ellipse_h40_s3", "ellipse_h12_s8_lf3", "open_quarter_h30_s2"])
+def test_replanning_regime_matches_reference_nodes(name):
+    """nodes/planner.py:17-102 + nodes/controller.py:28-94, run unmodified by oracle/gen_golden_replan.py around a
+    window-planner stub and the reference's own State.update, vs the oracle's restated re-planning loop: the planner's
+    index, the controller's index, steering, acceleration and the state, bit for bit, every tick."""
+    import json
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "replan_kat.json")) as f:
+        g = json.load(f)[name]
+    th = np.linspace(0, 2 * np.pi, 720, endpoint=False)
+    cx, cy = 40.0 * np.cos(th), 20.0 * np.sin(th)
+    curve = (40.0 * 20.0) / ((40.0 * np.sin(th)) ** 2 + (20.0 * np.cos(th)) ** 2) ** 1.5
+    if not g["closed"]:
+        cx, cy, curve = cx[:200], cy[:200], curve[:200]
+    p = loop.default_params()
+    p[loop.P_LF] = unhex(g["lf"])
+    spec = loop.RolloutSpec(steer="pure_pursuit", accel="pid", model="dynamic", max_steps=g["steps"],
+                            replan_horizon=g["horizon"], replan_stride=g["stride"], replan_after=3)
+    out = loop.rollout_episode(loop.Track(cx, cy, curve, closed=g["closed"]), spec, p, unhex(g["init"]))
+    n = out["steps"]                     # (the open path ends with PATH_END before the reference run was cut)
+    assert n == g["steps"] or (not g["closed"] and out["status"] & loop.ST_PATH_END)
+    assert n >= 100
+    assert list(out["ti"]) == g["ti"][:n]
+    assert_same(out["traj"], np.asarray(unhex(g["traj"]))[:n], "traj")
+    assert_same(out["steer"], unhex(g["steer"])[:n], "steer")
+    assert_same(out["accel"], unhex(g["accel"])[:n], "accel")
+    # the regime itself: with the stock look-ahead the planner re-plans on every tick; with a coarse path and a short
+    # controller look-ahead it holds a path for several ticks
+    replans = np.diff([0] + g["replans"])
+    assert replans.max() == 1 and (replans.min() == 1) == (name == "ellipse_h40_s3")
