@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- closed-loop sim-steps/sec of the batched rollout engine (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload pp_sweep|stanley_lqg|mpc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload pp_sweep|stanley_lqg|mpc|skidpad_mc|pp_replan]
 
 A "step" is ONE pass of the hot path over one batch of synthetic input: one ``bgr_rollout`` of E episodes x S
 closed-loop control steps (default workload = BASELINE config 2: the pure-pursuit look-ahead / PID-gain sweep,
@@ -35,14 +35,16 @@ UNIT = "sim-steps/s"
 
 # ncu --set full --clock-control none, one capture of the step kernel per change (profiles/r1_final/*.json)
 NCU_EVIDENCE = {
-    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 88.7,
-                 "sm_throughput_pct": 87.6, "pipe_fma_pct": 34.4, "pipe_alu_pct": 52.5, "pipe_xu_pct": 42.1,
-                 "pipe_fp64_pct": 6.7, "fp32_thread_inst_per_cycle_pct_of_peak": 27.2, "dram_throughput_pct": 0.10,
-                 "warp_inst_per_warp_step": 321.1, "registers": 64, "dram_bytes_per_launch": 167.2e6},
-    "stanley_lqg": {"file": "profiles/r1_final/ncu_full_stanley_lqg_dynamic.json", "issue_slots_busy_pct": 87.8,
-                    "sm_throughput_pct": 86.7, "pipe_fma_pct": 35.5, "pipe_alu_pct": 52.2, "pipe_xu_pct": 43.6,
-                    "pipe_fp64_pct": 6.4, "fp32_thread_inst_per_cycle_pct_of_peak": 25.5, "dram_throughput_pct": 0.09,
-                    "warp_inst_per_warp_step": 355.7, "registers": 64, "dram_bytes_per_launch": 167.2e6},
+    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 86.4,
+                 "sm_throughput_pct": 85.0, "pipe_fma_pct": 30.9, "pipe_fmaheavy_cycles_pct": 37.3, "pipe_alu_pct": 51.5,
+                 "pipe_xu_pct": 43.4, "pipe_fp64_pct": 6.1, "dram_throughput_pct": 0.11,
+                 "warp_inst_per_warp_step": 288.5, "registers": 64, "dram_bytes_per_launch": 169.1e6,
+                 "hot_lines": "profiles/r1_final/hot_lines_pp_pid_kinematic.txt"},
+    "stanley_lqg": {"file": "profiles/r1_final/ncu_full_stanley_lqg_dynamic.json", "issue_slots_busy_pct": 85.9,
+                    "sm_throughput_pct": 84.7, "pipe_fma_pct": 34.1, "pipe_fmaheavy_cycles_pct": 34.7,
+                    "pipe_alu_pct": 49.9, "pipe_xu_pct": 45.9, "pipe_fp64_pct": 6.5, "dram_throughput_pct": 0.10,
+                    "warp_inst_per_warp_step": 309.2, "registers": 64, "dram_bytes_per_launch": 168.7e6,
+                    "hot_lines": "profiles/r1_final/hot_lines_stanley_lqg_dynamic.txt"},
 }
 
 WORKLOADS = {
@@ -51,7 +53,12 @@ WORKLOADS = {
                  "config 2: pure-pursuit lookahead/gain sweep, 1Mi episodes x 2000 steps, stadium oval N=1024, 1 B200"),
     "stanley_lqg": ("stanley", "lqg", "dynamic", 1,
                     "config 3: Stanley + LQG + dynamic bicycle (tyre slip), episodes sharded over the GPUs"),
+    "pp_replan": ("pure_pursuit", "pid", "kinematic", 1,
+                  "SURVEY 8f.3: config 2's sweep in the live stack's re-planning regime (40-point local paths, every 3rd "
+                  "waypoint, re-planned when the planner's index passes 3: nodes/planner.py:26), full kernel build"),
 }
+# extra RolloutConfig / RolloutSpec fields per workload
+WORKLOAD_EXTRA = {"pp_replan": {"replan_horizon": 40, "replan_stride": 3, "replan_after": 3}}
 
 
 def parse_args():
@@ -78,10 +85,11 @@ def _cpu_worker(job):
     steer, accel, model, laps, _ = WORKLOADS[workload]
     ta = bgr.tracks.stadium_oval(1024)
     track = loop.Track(ta.x, ta.y, ta.kappa, True, ta.cones)
-    params = (bgr.sweeps.pp_sweep_params(count, start) if workload == "pp_sweep"
+    params = (bgr.sweeps.pp_sweep_params(count, start) if steer == "pure_pursuit"
               else bgr.sweeps.stanley_lqg_params(count, start=start))
     init = bgr.initial_states(ta, count, v0=5.0 if model == "dynamic" else 0.0)
-    spec = loop.RolloutSpec(steer=steer, accel=accel, model=model, max_steps=sim_steps, laps=laps)
+    spec = loop.RolloutSpec(steer=steer, accel=accel, model=model, max_steps=sim_steps, laps=laps,
+                            **WORKLOAD_EXTRA.get(workload, {}))
     done = 0
     t0 = time.perf_counter()
     for e in range(count):
@@ -120,7 +128,7 @@ def c_twin_sample(workload, sim_steps, episodes_per_core=4):
     try:
         import bgr_pathplanning_control_b200 as bgr
         from oracle import cport, loop
-        if not cport.available():
+        if not cport.available() or workload in WORKLOAD_EXTRA:
             return None
         steer, accel, model, laps, _ = WORKLOADS[workload]
         cores = len(os.sched_getaffinity(0))
@@ -290,11 +298,11 @@ def run_b200(args):
     ta = bgr.tracks.stadium_oval(1024)
     track = bgr.Track.from_arrays(ta, device=local)
     cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=laps,
-                            episode_id_base=rank * E)
+                            episode_id_base=rank * E, **WORKLOAD_EXTRA.get(args.workload, {}))
     # Input sets: each timed step consumes a DIFFERENT batch (rows of the sweep grid shifted by rank and set), so
     # the inputs touched over the timed region (n_sets x 112 B x E) exceed the 126 MB L2.
     n_sets = 4
-    make = bgr.sweeps.pp_sweep_params if args.workload == "pp_sweep" else \
+    make = bgr.sweeps.pp_sweep_params if steer == "pure_pursuit" else \
         (lambda n, start: bgr.sweeps.stanley_lqg_params(n, start=start))
     h_params = [torch.from_numpy(make(E, (rank * n_sets + s) * 65537)).pin_memory() for s in range(n_sets)]
     v0 = 5.0 if model == "dynamic" else 0.0     # the Euler-integrated tyre model is unstable below ~3.2 m/s
