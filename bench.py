@@ -479,8 +479,15 @@ def run_skidpad_mc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, bar
                                 torch.empty(abi.N_AGG, dtype=torch.float64, device=dev))
         jobs.append((cfg, torch.from_numpy(params).to(dev), torch.from_numpy(init).to(dev), out, params, init))
 
+    # the three kinds run on concurrent streams, the latency-bound Stanley kinds first (engine.rollout_groups);
+    # BGR_MC_SERIAL=1 launches them back to back on one stream instead
+    serial = os.environ.get("BGR_MC_SERIAL", "0") == "1"
+
     def step():
-        return [bgr.rollout(track, j[0], j[1], j[2], aggregate=True, out=j[3]) for j in jobs]
+        if serial:
+            return [bgr.rollout(track, j[0], j[1], j[2], aggregate=True, out=j[3]) for j in jobs]
+        return bgr.rollout_groups(track, [(j[0], j[1], j[2]) for j in jobs], aggregate=True,
+                                  outs=[j[3] for j in jobs], order=[2, 1, 0])
 
     for _ in range(args.warmup):
         step()
@@ -547,6 +554,8 @@ def run_skidpad_mc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, bar
                                    "perturbations (Philox4x32-10), NCCL metric gather", "episodes_per_gpu": per * len(kinds),
                        "kinds": ["+".join(k) for k in kinds], "sim_steps_cap": S, "track": "skidpad n=2048, 45 cones",
                        "cone_hits_last_step_rank0": hits, "parallelism": f"episode sharding x{world}",
+                       "launch": "kinds back to back on one stream" if serial else
+                                 "kinds on three concurrent streams, latency-bound Stanley kinds first",
                        "l2": "state lives in registers; 112 B in + 88 B out per episode"},
             "clocks": clocks,
             "e2e": {"value": float(se.item()) / float(te.item()), "unit": UNIT,

@@ -9,7 +9,7 @@ Importing the package does not load the CUDA library; the first call does and ra
 """
 from . import _abi, tracks, sweeps, sharding, roofline          # noqa: F401
 from .vehicle_config import Vehicle_config, conf               # noqa: F401
-from .engine import (Track, RolloutConfig, RolloutResult, MpcConfig, MpcResult, rollout, mpc_evaluate,   # noqa: F401
+from .engine import (Track, RolloutConfig, RolloutResult, MpcConfig, MpcResult, rollout, rollout_groups, mpc_evaluate,   # noqa: F401
                      default_params, initial_states, candidate_bank, lqg_design, fp32_peak_probe,
                      last_kernel_ms, launch_count, identify_dynamics)
 from .controllers import (PurePursuitController, StanleyController, ShadowedStanleyController, AccelerationPIDController,            # noqa: F401

@@ -287,6 +287,36 @@ def rollout(track, config, params, init_state, *, traj=False, aggregate=False, o
     return RolloutResult(metrics, status, tr, agg, ms)
 
 
+_group_streams = {}
+
+
+def rollout_groups(track, groups, *, aggregate=False, outs=None, order=None):
+    """Mixed-controller batches (BASELINE config 5): one homogeneous ``bgr_rollout`` per ``(config, params, init)``
+    group, the groups launched on CONCURRENT streams.  A group whose episodes end at very different times (noisy
+    Stanley on the skidpad: mean 130 steps, a few at the 1 500-step cap) spends most of its kernel time with a handful
+    of warps alive -- time another group's full-occupancy launch can fill.  ``order`` = launch order (default: as
+    given; put the latency-bound groups first).  CUDA tensors only; returns one ``RolloutResult`` per group, complete
+    on the CURRENT stream (the side streams are joined back into it)."""
+    torch = _torch()
+    dev = torch.device("cuda", track.device)
+    main = torch.cuda.current_stream(dev)
+    key = (track.device, len(groups))
+    if key not in _group_streams:
+        _group_streams[key] = [torch.cuda.Stream(dev) for _ in groups]
+    streams = _group_streams[key]
+    start = torch.cuda.Event()
+    start.record(main)
+    results = [None] * len(groups)
+    for g in (order if order is not None else range(len(groups))):
+        cfg, params, init = groups[g]
+        streams[g].wait_event(start)
+        with torch.cuda.stream(streams[g]):
+            results[g] = rollout(track, cfg, params, init, aggregate=aggregate, out=None if outs is None else outs[g])
+    for st in streams:
+        main.wait_stream(st)
+    return results
+
+
 def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out=None):
     params = _np(params, np.float32)
     E = params.shape[0]
