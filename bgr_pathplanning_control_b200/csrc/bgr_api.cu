@@ -304,6 +304,7 @@ extern "C" void bgr_track_destroy(bgr_track_t* t) {
   cudaFree(t->rival_range);
   cudaFree(t->rival_list);
   cudaFree(t->cone_range);
+  cudaFree(t->cone_near);
   cudaFree(t->cone_list);
   cudaFree(t->cones);
   for (auto& k : t->kf_tables) {
@@ -444,18 +445,23 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
 
   // cone candidate lists: cones within cone_reach of waypoint j
   std::vector<int32_t> cone_range(n, 0), cone_list;
+  std::vector<float> cone_near(n, 0.0f);   // distance from waypoint j to its closest listed cone, rounded DOWN
   std::vector<double2> cones(t->n_cones);
   for (int c = 0; c < t->n_cones; ++c) cones[c] = make_double2(desc->h_cones_xy[2 * c], desc->h_cones_xy[2 * c + 1]);
   if (t->n_cones > 0) {
     for (int j = 0; j < n; ++j) {
       const int first = static_cast<int>(cone_list.size());
       int cnt = 0;
+      double nearest_cone = desc->cone_reach;    // (an empty list: nothing closer than the reach)
       for (int c = 0; c < t->n_cones; ++c) {
-        if (std::hypot(cones[c].x - t->x[j], cones[c].y - t->y[j]) <= desc->cone_reach) {
+        const double dcw = std::hypot(cones[c].x - t->x[j], cones[c].y - t->y[j]);
+        if (dcw <= desc->cone_reach) {
           cone_list.push_back(c);
           ++cnt;
+          nearest_cone = std::min(nearest_cone, dcw);
         }
       }
+      cone_near[j] = std::nextafter(static_cast<float>(std::max(0.0, nearest_cone - 1e-4)), 0.0f);
       if (first >= (1 << 21)) {
         delete t;
         set_error("bgr_track_create: cone candidate lists overflow (cone_reach %.3f too large)", desc->cone_reach);
@@ -478,6 +484,7 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   if (rc == BGR_OK) rc = upload(&t->rival_list, rival_list);
   if (rc == BGR_OK && t->n_cones > 0) {
     rc = upload(&t->cone_range, cone_range);
+    if (rc == BGR_OK) rc = upload(&t->cone_near, cone_near);
     if (rc == BGR_OK) rc = upload(&t->cone_list, cone_list);
     if (rc == BGR_OK) rc = upload(&t->cones, cones);
   }
@@ -628,7 +635,8 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   bool attr_in_smem = true;
   if (!f64) {
     static const int force = [] { const char* e = std::getenv("BGR_ATTR_IN_SMEM"); return e ? std::atoi(e) : -1; }();
-    attr_in_smem = force >= 0 ? force != 0 : plan->smem <= kSmemAllTablesLimit;
+    // (the full build is register-limited to 2 CTAs per SM: it can afford twice the shared memory per CTA)
+    attr_in_smem = force >= 0 ? force != 0 : plan->smem <= (full ? 2 * kSmemAllTablesLimit : kSmemAllTablesLimit);
     if (!attr_in_smem) plan->smem = rollout_smem_bytes_xy_only(track->n_pad);
   }
   if (plan->smem > static_cast<size_t>(di.max_smem_optin)) {

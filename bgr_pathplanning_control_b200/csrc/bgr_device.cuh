@@ -53,6 +53,7 @@ struct TrackView {
   const int2* rival_range;    // [n] (first, count) into rival_list; count < 0: none
   const int2* rival_list;     // (waypoint, bits of its squared reach-in distance), ascending per list
   const int32_t* cone_range;  // [n] (first << 10) | count  into cone_list
+  const float* cone_near;     // [n] distance from waypoint j to its closest listed cone, rounded down
   const int32_t* cone_list;
   const double2* cones;       // [n_cones]
   int32_t n;
