@@ -531,9 +531,11 @@ def run_skidpad_mc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, bar
     w0 = time.perf_counter()
     e2e_steps = 0.0
     for _ in range(args.steps):
-        for j in jobs:
-            r = bgr.rollout(track, j[0], j[4], j[5], aggregate=True)
-            e2e_steps += float(r.aggregate[abi.A_STEPS])
+        if serial:
+            rs = [bgr.rollout(track, j[0], j[4], j[5], aggregate=True) for j in jobs]
+        else:
+            rs = bgr.rollout_groups(track, [(j[0], j[4], j[5]) for j in jobs], aggregate=True, order=[2, 1, 0])
+        e2e_steps += sum(float(r.aggregate[abi.A_STEPS]) for r in rs)
     e2e_s = time.perf_counter() - w0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     se = torch.tensor([e2e_steps], dtype=torch.float64, device=dev)

@@ -295,8 +295,16 @@ def rollout_groups(track, groups, *, aggregate=False, outs=None, order=None):
     group, the groups launched on CONCURRENT streams.  A group whose episodes end at very different times (noisy
     Stanley on the skidpad: mean 130 steps, a few at the 1 500-step cap) spends most of its kernel time with a handful
     of warps alive -- time another group's full-occupancy launch can fill.  ``order`` = launch order (default: as
-    given; put the latency-bound groups first).  CUDA tensors only; returns one ``RolloutResult`` per group, complete
-    on the CURRENT stream (the side streams are joined back into it)."""
+    given; put the latency-bound groups first).  CUDA tensors: one ``RolloutResult`` per group, complete on the
+    CURRENT stream (the side streams are joined back into it).  numpy arrays: one host thread per group through
+    ``bgr_rollout_host`` (ctypes drops the GIL; the library's copy / compute pipeline is per thread), synchronous."""
+    seq = list(order) if order is not None else list(range(len(groups)))
+    if any(isinstance(g[1], np.ndarray) or isinstance(g[2], np.ndarray) for g in groups):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(groups)) as pool:
+            futs = {g: pool.submit(rollout, track, groups[g][0], groups[g][1], groups[g][2], aggregate=aggregate,
+                                   out=None if outs is None else outs[g]) for g in seq}
+            return [futs[g].result() for g in range(len(groups))]
     torch = _torch()
     dev = torch.device("cuda", track.device)
     main = torch.cuda.current_stream(dev)
@@ -307,7 +315,7 @@ def rollout_groups(track, groups, *, aggregate=False, outs=None, order=None):
     start = torch.cuda.Event()
     start.record(main)
     results = [None] * len(groups)
-    for g in (order if order is not None else range(len(groups))):
+    for g in seq:
         cfg, params, init = groups[g]
         streams[g].wait_event(start)
         with torch.cuda.stream(streams[g]):

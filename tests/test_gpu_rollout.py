@@ -444,3 +444,38 @@ def test_rollout_groups_on_concurrent_streams_equal_serial_launches(cuda_device)
             assert torch.equal(a.status, b.status)
             assert torch.equal(a.metrics.view(torch.int32), b.metrics.view(torch.int32))
             assert torch.equal(a.aggregate.view(torch.int64), b.aggregate.view(torch.int64))
+
+
+@pytest.mark.parametrize("turns", [4, -3, 1000])
+@pytest.mark.parametrize("steer,accel,model", [("pure_pursuit", "pid", "kinematic"), ("stanley", "lqg", "dynamic")])
+def test_unwrapped_heading_far_from_zero(oval, turns, steer, accel, model):
+    """The reference never wraps yaw (car_state.py:217): an episode may start (or arrive) at a heading of many turns.
+    The production kernel integrates the heading in reduced form and restores the unwrapped value on output: the laws
+    see the same angles, the trajectory and the final yaw follow the oracle's unwrapped integration."""
+    ta, track = oval
+    cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1200, laps=2)
+    params = bgr.default_params(4)
+    v0 = 5.0 if model == "dynamic" else 1.0
+    init = bgr.initial_states(ta, 4, lateral_offset=np.linspace(-0.2, 0.2, 4), v0=v0)
+    init[:, abi.YAW] += turns * 2.0 * np.pi
+    res, worst = compare(ta, track, cfg, params, init, [0, 3])
+    ref_yaw = init[:, abi.YAW]
+    # one to two laps were driven: the final unwrapped yaw moved on by one or two turns
+    assert np.all(np.abs(res.metrics[:, abi.M_YAW] - ref_yaw) > 5.0)
+    assert np.all(np.abs(res.metrics[:, abi.M_YAW] - ref_yaw) < 4.5 * np.pi)
+
+
+def test_rollout_groups_from_host_buffers(cuda_device):
+    """numpy inputs: one host thread per group through bgr_rollout_host; same rows as one call per group."""
+    ta = bgr.tracks.stadium_oval(512)
+    track = bgr.Track.from_arrays(ta)
+    groups = []
+    for g, (steer, accel, model) in enumerate([("pure_pursuit", "pid", "kinematic"), ("stanley", "lqg", "dynamic")]):
+        E = 1500 + 37 * g
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=300, laps=2)
+        groups.append((cfg, bgr.sweeps.pp_sweep_params(E, g * 1000), bgr.initial_states(ta, E, v0=5.0)))
+    one = [bgr.rollout(track, *g, aggregate=True) for g in groups]
+    many = bgr.rollout_groups(track, groups, aggregate=True)
+    for a, b in zip(one, many):
+        assert np.array_equal(a.status, b.status) and np.array_equal(a.metrics.view(np.int32), b.metrics.view(np.int32))
+        assert np.array_equal(a.aggregate, b.aggregate)
