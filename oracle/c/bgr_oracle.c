@@ -41,6 +41,9 @@ typedef struct {
   double sigma_xy, sigma_yaw, sigma_v, sigma_cone;
   uint32_t seed, noise_on;
   int64_t episode_id_base;
+  /* re-planning replay (oracle/loop.py step 2'; nodes/planner.py:26,62,72-77); replan_horizon = 0: off */
+  int32_t replan_horizon, replan_stride, replan_after, reserved;
+  double planner_lookahead;
 } oracle_cfg_t;
 
 static const double PI = 3.141592653589793;
@@ -118,6 +121,8 @@ static void episode(const oracle_cfg_t* c, const double* cx, const double* cy, c
   int pid_has_last = 0;
   double xh0 = 0.0, xh1 = 0.0, P00 = 1.0, P01 = 0.0, P10 = 0.0, P11 = 1.0, a_prev = 0.0;
   long ti = 0;
+  long plan_org = -1, plan_ti = 0; /* Planner.current_path (its first waypoint) and Planner.target_ind */
+  const int replan = c->steer == 0 && c->replan_horizon > 0;
   int prev_near = -1, lap = 0, flags = 0, steps = 0, cone_hits = 0;
   double s_lat = 0, s_head = 0, max_lat = 0;
   /* two-pass std like numpy: keep the rows */
@@ -153,7 +158,38 @@ static void episode(const oracle_cfg_t* c, const double* cx, const double* cy, c
     /* 2. steering */
     double delta;
     long tim;
-    if (c->steer == 0) {
+    if (replan) {
+      const long M = c->replan_horizon, q = c->replan_stride;
+#define LOCAL_WP(kk) (c->closed ? (plan_org + q * (kk)) % n : ((plan_org + q * (kk)) < n - 1 ? (plan_org + q * (kk)) : n - 1))
+      if (plan_org < 0 || plan_ti > c->replan_after) { /* nodes/planner.py:26 */
+        long j0 = 0;
+        double best = hypot(cx[0] - ox, cy[0] - oy);
+        for (long i = 1; i < n; ++i) { /* the planned path starts at the waypoint nearest to the observed car */
+          double d = hypot(cx[i] - ox, cy[i] - oy);
+          if (d < best) { best = d; j0 = i; }
+        }
+        plan_org = j0;
+        plan_ti = 0; /* :62 */
+      }
+      while (plan_ti < M - 1) { /* the planner's own scan, :72-77 */
+        long m = LOCAL_WP(plan_ti);
+        if (hypot(cx[m] - ox, cy[m] - oy) >= c->planner_lookahead) break;
+        ++plan_ti;
+      }
+      ti = plan_ti; /* data["target_ind"], :101 */
+      while (ti < M) { /* core/controllers.py:212-218 on the local path */
+        long m = LOCAL_WP(ti);
+        if (hypot(cx[m] - ox, cy[m] - oy) >= p[P_LF]) break;
+        ++ti;
+      }
+      if (ti >= M) ti = M - 1; /* :219-220 */
+      tim = LOCAL_WP(ti);
+#undef LOCAL_WP
+      double alpha = atan2(cy[tim] - oy, cx[tim] - ox) - oyaw;
+      alpha = normalize_angle(alpha);
+      delta = atan2(2.0 * c->WB * sin(alpha) / p[P_LF], 1.0);
+      delta = clip(delta, -c->max_steer, c->max_steer);
+    } else if (c->steer == 0) {
       while (ti < n_tot) { /* :212-218 on the unrolled (tiled) path */
         long m = ti % n;
         double d = hypot(cx[m] - ox, cy[m] - oy);
@@ -267,7 +303,8 @@ static void episode(const oracle_cfg_t* c, const double* cx, const double* cy, c
     steps = k + 1;
     if (!(isfinite(x) && isfinite(y) && isfinite(yaw) && isfinite(v) && isfinite(r) && isfinite(beta)))
       flags |= ST_NONFINITE;
-    if (c->steer == 0 && ti >= n_tot - 1) flags |= ST_PATH_END;
+    if (c->steer == 0 && !replan && ti >= n_tot - 1) flags |= ST_PATH_END;
+    if (replan && !c->closed && tim >= n - 1) flags |= ST_PATH_END;
     if (c->steer == 1 && !c->closed && ti >= n_tot - 1) flags |= ST_PATH_END;
     if (c->laps_target > 0 && lap >= c->laps_target) flags |= ST_LAPS_DONE;
     if (flags) break;

@@ -27,7 +27,9 @@ class Cfg(C.Structure):
                 ("hit_radius", C.c_double), ("lqr_k0", C.c_double), ("lqr_k1", C.c_double),
                 ("sigma_xy", C.c_double), ("sigma_yaw", C.c_double), ("sigma_v", C.c_double),
                 ("sigma_cone", C.c_double), ("seed", C.c_uint32), ("noise_on", C.c_uint32),
-                ("episode_id_base", C.c_int64)]
+                ("episode_id_base", C.c_int64),
+                ("replan_horizon", C.c_int32), ("replan_stride", C.c_int32), ("replan_after", C.c_int32),
+                ("reserved", C.c_int32), ("planner_lookahead", C.c_double)]
 
 
 _lib = None
@@ -75,6 +77,8 @@ def rollout(track: loop.Track, spec: loop.RolloutSpec, params, init, episode_id_
         c.sigma_xy, c.sigma_yaw, c.sigma_v, c.sigma_cone = nz.sigma_xy, nz.sigma_yaw, nz.sigma_v, nz.sigma_cone
         c.seed, c.noise_on = nz.seed & 0xFFFFFFFF, 1
     c.episode_id_base = episode_id_base
+    c.replan_horizon, c.replan_stride, c.replan_after = spec.replan_horizon, spec.replan_stride, spec.replan_after
+    c.planner_lookahead = conf.LOOKAHEAD_DISTANCE
     metrics = np.empty((E, N_METRICS))
     status = np.empty((E, N_STATUS), dtype=np.int32)
     tr = np.zeros((E, spec.max_steps, N_TRAJ)) if traj else None

@@ -116,3 +116,41 @@ def test_replay_is_rejected_where_it_is_undefined(cuda_device):
                     bgr.initial_states(ta, 1))
     with pytest.raises(abi.BgrError):
         bgr.rollout(track, bgr.RolloutConfig(replan_horizon=1), bgr.default_params(1), bgr.initial_states(ta, 1))
+
+
+def test_replay_at_scale_against_the_c_twin(cuda_device):
+    """512 episodes x 2 000 steps of config 2's sweep rows in the re-planning regime: fp32 production kernel (the
+    replay runs in the audited full build) vs the plain-C fp64 twin.  As in test_parity_at_scale_against_the_c_twin:
+    every index mismatch must be covered by the kernel's near-tie audit channel; well-conditioned unflagged episodes
+    end within the north-star tolerances."""
+    from oracle import cport
+    from test_gpu_rollout import OFF_TRACK_M, POS_TOL, YAW_TOL, LAP_TOL, otrack
+    ta = bgr.tracks.stadium_oval(1024)
+    track = bgr.Track.from_arrays(ta)
+    E, S = 512, 2000
+    params = bgr.sweeps.pp_sweep_params(E, start=32 * 16384 + 4242)
+    init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.3, 0.3, E))
+    cfg = bgr.RolloutConfig(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=S, replan_horizon=40,
+                            replan_stride=3)
+    res = bgr.rollout(track, cfg, params, init)
+    spec = loop.RolloutSpec(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=S, replan_horizon=40,
+                            replan_stride=3, replan_after=3)
+    p64 = params.astype(np.float64)
+    m, s, _ = cport.rollout(otrack(ta), spec, p64, init)
+    nudged = init.copy()
+    nudged[:, abi.X] += 1e-7
+    m2, _, _ = cport.rollout(otrack(ta), spec, p64, nudged)
+    well = np.hypot(m2[:, 6] - m[:, 6], m2[:, 7] - m[:, 7]) < 1e-5
+    on_track = (m[:, 5] < OFF_TRACK_M) & (res.metrics[:, abi.M_MAX_ABS_LAT] < OFF_TRACK_M)
+    unflagged = res.status[:, abi.S_NEAR_TIES] == 0
+    good = on_track & well & unflagged
+    assert on_track.mean() > 0.4 and good.sum() > E // 8, (on_track.mean(), well.mean(), unflagged.mean(), good.sum())
+    cols = [abi.S_FLAGS, abi.S_STEPS, abi.S_TARGET_IND, abi.S_NEAREST_IND, abi.S_LAPS]
+    mism = np.any(res.status[:, cols] != s[:, cols], axis=1)
+    assert not np.any(mism & good), f"{(mism & good).sum()} index mismatches without a flagged near-tie"
+    dpos = np.hypot(res.metrics[:, abi.M_X] - m[:, 6], res.metrics[:, abi.M_Y] - m[:, 7])
+    dyaw = np.abs(res.metrics[:, abi.M_YAW] - m[:, 8])
+    assert dpos[good].max() < POS_TOL and dyaw[good].max() < YAW_TOL, (dpos[good].max(), dyaw[good].max())
+    assert np.abs(res.metrics[good, abi.M_LAP_TIME] - m[good, 4]).max() < LAP_TOL
+    assert np.abs(res.metrics[good, abi.M_LAT_MEAN] - m[good, 0]).max() < 1e-4
+    assert res.status[:, abi.S_LAPS].max() >= 2

@@ -59,6 +59,31 @@ def test_c_twin_equals_numpy_oracle(steer, accel, model, laps, laps_target, trac
         np.testing.assert_allclose(m[e, 6:12], ref["state"], rtol=0, atol=1e-8)
 
 
+@pytest.mark.parametrize("trackname,horizon,stride", [("oval", 40, 3), ("oval", 12, 8), ("skidpad", 30, 2)])
+def test_c_twin_replanning_regime(trackname, horizon, stride):
+    """Re-planning replay (oracle/loop.py step 2'): same local-path windows, planner index and controller index."""
+    import bgr_pathplanning_control_b200 as bgr
+    ta, tr = _oval() if trackname == "oval" else _skidpad()
+    E, S = 6, 500
+    rng = np.random.default_rng(6)
+    params = np.tile(loop.default_params(), (E, 1))
+    params[:, loop.P_LF] = rng.uniform(2.5, 7.0, E)
+    init = bgr.initial_states(ta, E, lateral_offset=rng.uniform(-0.4, 0.4, E), v0=2.0)
+    if trackname == "skidpad":
+        init[:, 2] = 0.0
+    noise = loop.NoiseSpec(seed=17, sigma_xy=0.03, sigma_yaw=0.005, sigma_v=0.05)
+    spec = loop.RolloutSpec(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=S, laps_target=1,
+                            noise=noise, replan_horizon=horizon, replan_stride=stride, replan_after=3)
+    m, s, t = cport.rollout(tr, spec, params, init, episode_id_base=7, traj=True, threads=2)
+    for e in range(E):
+        ref = loop.rollout_episode(tr, spec, params[e], init[e], episode_id=7 + e)
+        n = ref["steps"]
+        assert s[e, 1] == n and s[e, 0] == ref["status"] and s[e, 2] == ref["target_ind"] and s[e, 5] == ref["laps"]
+        assert np.array_equal(t[e, :n, 8].astype(int), ref["ti"]) and np.array_equal(t[e, :n, 9].astype(int), ref["near"])
+        np.testing.assert_allclose(t[e, :n, :6], ref["traj"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(t[e, :n, 6], ref["steer"], rtol=0, atol=1e-10)
+
+
 def test_c_twin_edge_cases():
     import bgr_pathplanning_control_b200 as bgr
     ta, tr = _oval()
