@@ -242,47 +242,75 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(const __grid_constant_
 // 64-bit atomicMin on (cost bits << 32 | index): order independent, lowest index wins exact ties like np.argmin.
 constexpr int kFactThreads = 256;
 constexpr int kFactSlices = kFactThreads / 32;
-constexpr int kFactChunk = 1024;                 // candidates staged per pass: 1024 x 40 B = 40 KB => 5 CTAs per SM
+constexpr int kFactChunk = 256;                  // candidates per CTA (10 KB of statistics)
+constexpr int kFactEpisodes = 64;                // episodes per CTA: TWO per lane
 
+// One CTA scores 64 episodes x 256 candidates.  Lane l of every warp owns episodes l and l + 32 of the CTA's block:
+// a candidate's five statistics are read from shared memory ONCE (broadcast) and used for two cost evaluations -- the
+// first version (one episode per lane, all K candidates per CTA) was bound by exactly those loads (ncu: LSU pipe
+// 66 % busy, 24 instructions per pair).  The eight warps take every eighth candidate; their winners are merged
+// through shared memory, then one 64-bit atomicMin per episode merges the candidate chunks (grid.y).
+// grid = (ceil(E / 64), ceil(K / 256)): 4 096 small CTAs for config 4 -- 7 waves of 148 x 4, no tail to speak of.
 __global__ void __launch_bounds__(kFactThreads) mpc_factored_kernel(const CandStats* __restrict__ cand,
                                                                     const EpiCoef* __restrict__ epi, int K,
                                                                     long long n_episodes,
                                                                     unsigned long long* __restrict__ packed,
                                                                     float* __restrict__ costs) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CandStats* s_c = reinterpret_cast<CandStats*>(smem_raw);
+  __shared__ __align__(16) CandStats s_c[kFactChunk];
+  __shared__ unsigned long long s_best[kFactSlices][kFactEpisodes];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const long long e = static_cast<long long>(blockIdx.x) * 32 + lane;
-  const bool evalid = e < n_episodes;
-  const EpiCoef ec = epi[evalid ? e : 0];
-  float best = INFINITY;
-  int best_i = -1;
-  for (int c0 = 0; c0 < K; c0 += kFactChunk) {
-    const int nc = min(kFactChunk, K - c0);
-    __syncthreads();
-    {  // coalesced copy of the chunk (5 doubles per candidate)
-      const double* src = reinterpret_cast<const double*>(cand + c0);
-      double* dst = reinterpret_cast<double*>(s_c);
-      for (int i = threadIdx.x; i < nc * 5; i += kFactThreads) dst[i] = src[i];
-    }
-    __syncthreads();
+  const long long e_a = static_cast<long long>(blockIdx.x) * kFactEpisodes + lane, e_b = e_a + 32;
+  const bool valid_a = e_a < n_episodes, valid_b = e_b < n_episodes;
+  const EpiCoef ea = epi[valid_a ? e_a : 0], eb = epi[valid_b ? e_b : 0];
+  const int c0 = blockIdx.y * kFactChunk;
+  const int nc = min(kFactChunk, K - c0);
+  {  // coalesced copy of the chunk (5 doubles per candidate)
+    const double* src = reinterpret_cast<const double*>(cand + c0);
+    double* dst = reinterpret_cast<double*>(s_c);
+    for (int i = threadIdx.x; i < nc * 5; i += kFactThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  float best_a = INFINITY, best_b = INFINITY;
+  int idx_a = -1, idx_b = -1;
+  auto score = [](const EpiCoef& ec, const CandStats& cs) -> float {
+    // two independent FMA pairs (shorter dependency chain than a 4-deep Horner form)
+    const double J = fma(ec.C1, cs.SS, ec.C0 + cs.G) + fma(ec.C3, cs.SA, ec.C2 * cs.SS2);
+    float costf = static_cast<float>(J);
+    if (!(ec.v0 >= cs.vreq) || !(costf == costf)) costf = INFINITY;             // infeasible (:536) / NaN
+    return fmaxf(costf, 0.0f);                                                 // round-off below an exact zero
+  };
 #pragma unroll 4
-    for (int c = slice; c < nc; c += kFactSlices) {
-      const CandStats cs = s_c[c];
-      // two independent FMA pairs (shorter dependency chain than a 4-deep Horner form)
-      const double J = fma(ec.C1, cs.SS, ec.C0 + cs.G) + fma(ec.C3, cs.SA, ec.C2 * cs.SS2);
-      float costf = static_cast<float>(J);
-      if (!(ec.v0 >= cs.vreq) || !(costf == costf)) costf = INFINITY;           // infeasible (:536) / NaN
-      costf = fmaxf(costf, 0.0f);                                               // round-off below an exact zero
-      if (costs != nullptr && evalid) costs[static_cast<size_t>(e) * K + c0 + c] = costf;
-      if (costf < best) {
-        best = costf;
-        best_i = c0 + c;
-      }
+  for (int c = slice; c < nc; c += kFactSlices) {
+    const CandStats cs = s_c[c];
+    const float ca = score(ea, cs), cb = score(eb, cs);
+    if (costs != nullptr) {
+      if (valid_a) costs[static_cast<size_t>(e_a) * K + c0 + c] = ca;
+      if (valid_b) costs[static_cast<size_t>(e_b) * K + c0 + c] = cb;
+    }
+    if (ca < best_a) {        // ascending c: strict < keeps the first minimum
+      best_a = ca;
+      idx_a = c0 + c;
+    }
+    if (cb < best_b) {
+      best_b = cb;
+      idx_b = c0 + c;
     }
   }
-  if (evalid && best < INFINITY)
-    atomicMin(packed + e, (static_cast<unsigned long long>(__float_as_uint(best)) << 32) | static_cast<uint32_t>(best_i));
+  // (cost bits << 32 | index): costs are >= 0, so the packed words order like (cost, index); ~0 = nothing feasible
+  auto pack = [](float best, int idx) -> unsigned long long {
+    return best < INFINITY ? (static_cast<unsigned long long>(__float_as_uint(best)) << 32) | static_cast<uint32_t>(idx)
+                           : ~0ull;
+  };
+  s_best[slice][lane] = pack(best_a, idx_a);
+  s_best[slice][lane + 32] = pack(best_b, idx_b);
+  __syncthreads();
+  if (threadIdx.x < kFactEpisodes) {
+    unsigned long long m = s_best[0][threadIdx.x];
+#pragma unroll
+    for (int sl = 1; sl < kFactSlices; ++sl) m = min(m, s_best[sl][threadIdx.x]);
+    const long long e = static_cast<long long>(blockIdx.x) * kFactEpisodes + threadIdx.x;
+    if (e < n_episodes && m != ~0ull) atomicMin(packed + e, m);
+  }
 }
 
 cudaError_t launch_mpc_factored(const MpcArgs& A, void* scratch_cand, void* scratch_epi, cudaStream_t stream,
@@ -293,12 +321,10 @@ cudaError_t launch_mpc_factored(const MpcArgs& A, void* scratch_cand, void* scra
   const int cand_blocks = (A.K + 127) / 128;
   const unsigned epi_blocks = static_cast<unsigned>((A.n_episodes + 127) / 128);
   mpc_prepare_kernel<<<cand_blocks + epi_blocks, 128, 0, stream>>>(A, cand_blocks, cand, epi);
-  const size_t smem = static_cast<size_t>(A.K < kFactChunk ? A.K : kFactChunk) * sizeof(CandStats);
-  cudaError_t err = cudaFuncSetAttribute(mpc_factored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
-  const unsigned grid = static_cast<unsigned>((A.n_episodes + 31) / 32);
-  mpc_factored_kernel<<<grid, kFactThreads, smem, stream>>>(cand, epi, A.K, A.n_episodes, A.packed, A.costs);
+  const long long chunks = (A.K + kFactChunk - 1) / kFactChunk;
+  if (chunks > 65535) return cudaErrorInvalidValue;   // K < 16.7 M candidates
+  const dim3 grid(static_cast<unsigned>((A.n_episodes + kFactEpisodes - 1) / kFactEpisodes), static_cast<unsigned>(chunks));
+  mpc_factored_kernel<<<grid, kFactThreads, 0, stream>>>(cand, epi, A.K, A.n_episodes, A.packed, A.costs);
   return cudaGetLastError();
 }
 
