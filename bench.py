@@ -35,15 +35,15 @@ UNIT = "sim-steps/s"
 
 # ncu --set full --clock-control none, one capture of the step kernel per change (profiles/r1_final/*.json)
 NCU_EVIDENCE = {
-    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 86.4,
-                 "sm_throughput_pct": 85.0, "pipe_fma_pct": 30.9, "pipe_fmaheavy_cycles_pct": 37.3, "pipe_alu_pct": 51.5,
-                 "pipe_xu_pct": 43.4, "pipe_fp64_pct": 6.1, "dram_throughput_pct": 0.11,
-                 "warp_inst_per_warp_step": 288.5, "registers": 64, "dram_bytes_per_launch": 169.1e6,
+    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 87.0,
+                 "sm_throughput_pct": 85.7, "pipe_fma_pct": 31.3, "pipe_fmaheavy_cycles_pct": 37.9, "pipe_alu_pct": 51.4,
+                 "pipe_xu_pct": 43.3, "pipe_fp64_pct": 6.0, "dram_throughput_pct": 0.11,
+                 "warp_inst_per_warp_step": 291.0, "registers": 64, "dram_bytes_per_launch": 169.0e6,
                  "hot_lines": "profiles/r1_final/hot_lines_pp_pid_kinematic.txt"},
-    "stanley_lqg": {"file": "profiles/r1_final/ncu_full_stanley_lqg_dynamic.json", "issue_slots_busy_pct": 85.9,
-                    "sm_throughput_pct": 84.7, "pipe_fma_pct": 34.1, "pipe_fmaheavy_cycles_pct": 34.7,
-                    "pipe_alu_pct": 49.9, "pipe_xu_pct": 45.9, "pipe_fp64_pct": 6.5, "dram_throughput_pct": 0.10,
-                    "warp_inst_per_warp_step": 309.2, "registers": 64, "dram_bytes_per_launch": 168.7e6,
+    "stanley_lqg": {"file": "profiles/r1_final/ncu_full_stanley_lqg_dynamic.json", "issue_slots_busy_pct": 86.1,
+                    "sm_throughput_pct": 84.9, "pipe_fma_pct": 34.2, "pipe_fmaheavy_cycles_pct": 33.5,
+                    "pipe_alu_pct": 50.6, "pipe_xu_pct": 47.0, "pipe_fp64_pct": 6.6, "dram_throughput_pct": 0.10,
+                    "warp_inst_per_warp_step": 303.1, "registers": 64, "dram_bytes_per_launch": 169.2e6,
                     "hot_lines": "profiles/r1_final/hot_lines_stanley_lqg_dynamic.txt"},
 }
 
