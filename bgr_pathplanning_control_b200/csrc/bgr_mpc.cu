@@ -201,17 +201,24 @@ __device__ __forceinline__ void episode_coef(const MpcArgs& A, EpiCoef* __restri
   int len = A.ref_len != nullptr ? A.ref_len[e] : (A.trk.closed ? 0x3fffffff : n - start);
   if (len < 1) len = 1;
   double sx = x0, sy = y0, XY = 0.0;
+  // reference point of stage t: waypoint start + min(t, H - 1, len - 1), modulo n (closed) or clipped (open); the
+  // index is carried incrementally (one 64-bit modulo per episode instead of one per stage)
+  const int last_ref = min(A.H - 1, len - 1);
+  long long idx = static_cast<long long>(start);
+  if (A.trk.closed) idx %= n;
+  else if (idx > n - 1) idx = n - 1;
+  int wp = static_cast<int>(idx);
+  const double step_x = v0 * cos_t * A.dt, step_y = v0 * sin_t * A.dt;
   for (int t = 0; t <= A.H; ++t) {                                  // stages 0..H-1 and the terminal term (:548)
-    int k_ref = t < A.H ? t : A.H - 1;
-    if (k_ref >= len) k_ref = len - 1;
-    long long idx = static_cast<long long>(start) + k_ref;
-    if (A.trk.closed) idx %= n;
-    else if (idx > n - 1) idx = n - 1;
-    const double2 p = A.trk.xy_d[idx];
+    const double2 p = A.trk.xy_d[wp];
     const double ex = sx - p.x, ey = sy - p.y;
     XY += A.q0 * ex * ex + A.q1 * ey * ey;
-    sx = sx + v0 * cos_t * A.dt;                                    // :523
-    sy = sy + v0 * sin_t * A.dt;                                    // :524
+    sx = sx + step_x;                                               // :523
+    sy = sy + step_y;                                               // :524
+    if (t < last_ref) {
+      ++wp;
+      if (wp >= n) wp = A.trk.closed ? 0 : n - 1;
+    }
   }
   const double cyw = v0 / A.wheelbase;                              // yaw_k = yaw0 + cyw * S_k
   const double ev0 = v0 - A.target_speed;
