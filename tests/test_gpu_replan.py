@@ -154,3 +154,24 @@ def test_replay_at_scale_against_the_c_twin(cuda_device):
     assert np.abs(res.metrics[good, abi.M_LAP_TIME] - m[good, 4]).max() < LAP_TOL
     assert np.abs(res.metrics[good, abi.M_LAT_MEAN] - m[good, 0]).max() < 1e-4
     assert res.status[:, abi.S_LAPS].max() >= 2
+
+
+def test_replay_through_host_buffers_and_two_phase_launches(cuda_device):
+    """The replay is plain episode state: the host-buffer entry point (chunked, pipelined) and a two-phase launch
+    (cfg.split_steps) return the rows of the single device launch bit for bit."""
+    import torch
+    ta = bgr.tracks.stadium_oval(1024)
+    track = bgr.Track.from_arrays(ta)
+    E = 3000
+    params = bgr.sweeps.pp_sweep_params(E, start=32 * 16384)
+    init = bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.3, 0.3, E))
+    kw = dict(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=500, laps_target=1, replan_horizon=25,
+              replan_stride=4)
+    dev = bgr.rollout(track, bgr.RolloutConfig(**kw), torch.from_numpy(params).to(cuda_device),
+                      torch.from_numpy(init).to(cuda_device), aggregate=True)
+    host = bgr.rollout(track, bgr.RolloutConfig(**kw), params, init, aggregate=True)
+    split = bgr.rollout(track, bgr.RolloutConfig(split_steps=120, **kw), params, init, aggregate=True)
+    for other in (host, split):
+        assert np.array_equal(dev.status.cpu().numpy(), other.status)
+        assert np.array_equal(dev.metrics.cpu().numpy().view(np.int32), other.metrics.view(np.int32))
+        assert np.array_equal(dev.aggregate.cpu().numpy(), other.aggregate)
