@@ -35,10 +35,10 @@ UNIT = "sim-steps/s"
 
 # ncu --set full --clock-control none, one capture of the step kernel per change (profiles/r1_final/*.json)
 NCU_EVIDENCE = {
-    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 87.0,
-                 "sm_throughput_pct": 85.7, "pipe_fma_pct": 31.3, "pipe_fmaheavy_cycles_pct": 37.9, "pipe_alu_pct": 51.4,
-                 "pipe_xu_pct": 43.3, "pipe_fp64_pct": 6.0, "dram_throughput_pct": 0.11,
-                 "warp_inst_per_warp_step": 291.0, "registers": 64, "dram_bytes_per_launch": 169.0e6,
+    "pp_sweep": {"file": "profiles/r1_final/ncu_full_pp_pid_kinematic.json", "issue_slots_busy_pct": 86.6,
+                 "sm_throughput_pct": 85.2, "pipe_fma_pct": 28.5, "pipe_fmaheavy_cycles_pct": 35.8, "pipe_alu_pct": 51.5,
+                 "pipe_xu_pct": 46.7, "pipe_fp64_pct": 6.5, "dram_throughput_pct": 0.12,
+                 "warp_inst_per_warp_step": 269.1, "registers": 64, "dram_bytes_per_launch": 169.1e6,
                  "hot_lines": "profiles/r1_final/hot_lines_pp_pid_kinematic.txt"},
     "stanley_lqg": {"file": "profiles/r1_final/ncu_full_stanley_lqg_dynamic.json", "issue_slots_busy_pct": 86.1,
                     "sm_throughput_pct": 84.9, "pipe_fma_pct": 34.2, "pipe_fmaheavy_cycles_pct": 33.5,
