@@ -56,7 +56,19 @@ class WindowPlanner:
         return path, empty, empty, empty, empty, np.zeros(0, int), np.zeros(0, int)
 
 
+_nodes = None
+
+
 def load_nodes():
+    """(reference namespace, nodes.planner, nodes.controller, list the stubbed simulator call appends to); cached --
+    the node modules bind the stub functions at import time."""
+    global _nodes
+    if _nodes is None:
+        _nodes = _load_nodes()
+    return _nodes
+
+
+def _load_nodes():
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import ref_shim
     ref = ref_shim.load_reference()
