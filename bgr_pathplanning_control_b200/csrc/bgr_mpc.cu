@@ -250,14 +250,18 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(const __grid_constant_
 constexpr int kFactThreads = 256;
 constexpr int kFactSlices = kFactThreads / 32;
 constexpr int kFactChunk = 256;                  // candidates per CTA (10 KB of statistics)
-constexpr int kFactEpisodes = 64;                // episodes per CTA: TWO per lane
+#ifndef BGR_MPC_EPISODES_PER_LANE
+#define BGR_MPC_EPISODES_PER_LANE 4   // measured on config 4: 1 -> 88 us (first version), 2 -> 50 us, 4 -> 46 us
+#endif
+constexpr int kFactPerLane = BGR_MPC_EPISODES_PER_LANE;   // episodes per lane
+constexpr int kFactEpisodes = 32 * kFactPerLane;          // episodes per CTA
 
-// One CTA scores 64 episodes x 256 candidates.  Lane l of every warp owns episodes l and l + 32 of the CTA's block:
-// a candidate's five statistics are read from shared memory ONCE (broadcast) and used for two cost evaluations -- the
-// first version (one episode per lane, all K candidates per CTA) was bound by exactly those loads (ncu: LSU pipe
-// 66 % busy, 24 instructions per pair).  The eight warps take every eighth candidate; their winners are merged
-// through shared memory, then one 64-bit atomicMin per episode merges the candidate chunks (grid.y).
-// grid = (ceil(E / 64), ceil(K / 256)): 4 096 small CTAs for config 4 -- 7 waves of 148 x 4, no tail to speak of.
+// One CTA scores 128 episodes x 256 candidates.  Lane l of every warp owns episodes l, l + 32, l + 64, l + 96 of the
+// CTA's block: a candidate's five statistics are read from shared memory ONCE (broadcast) and used for four cost
+// evaluations -- the first version (one episode per lane, all K candidates per CTA) was bound by exactly those loads
+// (ncu: LSU pipe 66 % busy, 24 instructions per pair).  The eight warps take every eighth candidate; their winners
+// are merged through shared memory, then one 64-bit atomicMin per episode merges the candidate chunks (grid.y).
+// grid = (ceil(E / 128), ceil(K / 256)): 2 048 small CTAs for config 4 -- 7 waves of 148 x 2, no tail to speak of.
 __global__ void __launch_bounds__(kFactThreads) mpc_factored_kernel(const CandStats* __restrict__ cand,
                                                                     const EpiCoef* __restrict__ epi, int K,
                                                                     long long n_episodes,
@@ -266,9 +270,17 @@ __global__ void __launch_bounds__(kFactThreads) mpc_factored_kernel(const CandSt
   __shared__ __align__(16) CandStats s_c[kFactChunk];
   __shared__ unsigned long long s_best[kFactSlices][kFactEpisodes];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const long long e_a = static_cast<long long>(blockIdx.x) * kFactEpisodes + lane, e_b = e_a + 32;
-  const bool valid_a = e_a < n_episodes, valid_b = e_b < n_episodes;
-  const EpiCoef ea = epi[valid_a ? e_a : 0], eb = epi[valid_b ? e_b : 0];
+  const long long e_first = static_cast<long long>(blockIdx.x) * kFactEpisodes + lane;   // + 32 r for r = 0..
+  EpiCoef ec[kFactPerLane];
+  float best[kFactPerLane];
+  int best_i[kFactPerLane];
+#pragma unroll
+  for (int r = 0; r < kFactPerLane; ++r) {
+    const long long e = e_first + 32 * r;
+    ec[r] = epi[e < n_episodes ? e : 0];
+    best[r] = INFINITY;
+    best_i[r] = -1;
+  }
   const int c0 = blockIdx.y * kFactChunk;
   const int nc = min(kFactChunk, K - c0);
   {  // coalesced copy of the chunk (5 doubles per candidate)
@@ -277,39 +289,32 @@ __global__ void __launch_bounds__(kFactThreads) mpc_factored_kernel(const CandSt
     for (int i = threadIdx.x; i < nc * 5; i += kFactThreads) dst[i] = src[i];
   }
   __syncthreads();
-  float best_a = INFINITY, best_b = INFINITY;
-  int idx_a = -1, idx_b = -1;
-  auto score = [](const EpiCoef& ec, const CandStats& cs) -> float {
-    // two independent FMA pairs (shorter dependency chain than a 4-deep Horner form)
-    const double J = fma(ec.C1, cs.SS, ec.C0 + cs.G) + fma(ec.C3, cs.SA, ec.C2 * cs.SS2);
-    float costf = static_cast<float>(J);
-    if (!(ec.v0 >= cs.vreq) || !(costf == costf)) costf = INFINITY;             // infeasible (:536) / NaN
-    return fmaxf(costf, 0.0f);                                                 // round-off below an exact zero
-  };
 #pragma unroll 4
   for (int c = slice; c < nc; c += kFactSlices) {
     const CandStats cs = s_c[c];
-    const float ca = score(ea, cs), cb = score(eb, cs);
-    if (costs != nullptr) {
-      if (valid_a) costs[static_cast<size_t>(e_a) * K + c0 + c] = ca;
-      if (valid_b) costs[static_cast<size_t>(e_b) * K + c0 + c] = cb;
-    }
-    if (ca < best_a) {        // ascending c: strict < keeps the first minimum
-      best_a = ca;
-      idx_a = c0 + c;
-    }
-    if (cb < best_b) {
-      best_b = cb;
-      idx_b = c0 + c;
+#pragma unroll
+    for (int r = 0; r < kFactPerLane; ++r) {
+      // two independent FMA pairs (shorter dependency chain than a 4-deep Horner form)
+      const double J = fma(ec[r].C1, cs.SS, ec[r].C0 + cs.G) + fma(ec[r].C3, cs.SA, ec[r].C2 * cs.SS2);
+      float costf = static_cast<float>(J);
+      if (!(ec[r].v0 >= cs.vreq) || !(costf == costf)) costf = INFINITY;         // infeasible (:536) / NaN
+      costf = fmaxf(costf, 0.0f);                                               // round-off below an exact zero
+      if (costs != nullptr) {
+        const long long e = e_first + 32 * r;
+        if (e < n_episodes) costs[static_cast<size_t>(e) * K + c0 + c] = costf;
+      }
+      if (costf < best[r]) {    // ascending c: strict < keeps the first minimum
+        best[r] = costf;
+        best_i[r] = c0 + c;
+      }
     }
   }
   // (cost bits << 32 | index): costs are >= 0, so the packed words order like (cost, index); ~0 = nothing feasible
-  auto pack = [](float best, int idx) -> unsigned long long {
-    return best < INFINITY ? (static_cast<unsigned long long>(__float_as_uint(best)) << 32) | static_cast<uint32_t>(idx)
+#pragma unroll
+  for (int r = 0; r < kFactPerLane; ++r)
+    s_best[slice][lane + 32 * r] =
+        best[r] < INFINITY ? (static_cast<unsigned long long>(__float_as_uint(best[r])) << 32) | static_cast<uint32_t>(best_i[r])
                            : ~0ull;
-  };
-  s_best[slice][lane] = pack(best_a, idx_a);
-  s_best[slice][lane + 32] = pack(best_b, idx_b);
   __syncthreads();
   if (threadIdx.x < kFactEpisodes) {
     unsigned long long m = s_best[0][threadIdx.x];
