@@ -54,7 +54,24 @@ def test_reference_nodes_golden_run(cuda_device, name, precision):
     else:   # the open path ends when the target is its last waypoint (the reference run was simply cut later)
         assert res.status[0, abi.S_FLAGS] == abi.ST_PATH_END and 100 <= n < g["steps"]
     tr = res.traj[0, :n]
-    assert list(tr[:, abi.T_TARGET_IND].astype(int)) == g["ti"][:n]          # the controller's LOCAL index, exact
+    got_ti = tr[:, abi.T_TARGET_IND].astype(int)
+    if precision == "fp64":
+        assert list(got_ti) == g["ti"][:n]                                   # the controller's LOCAL index, exact
+    else:
+        # fp32 laws: an index may differ only at an exact-distance near-tie of the ORACLE's own run (margin < 2e-5 m);
+        # beyond such a step the two runs are different episodes, so the comparison stops there
+        bad = np.nonzero(got_ti != np.asarray(g["ti"][:n]))[0]
+        if len(bad):
+            p64 = loop.default_params()
+            p64[loop.P_LF] = unhex(g["lf"])
+            spec = loop.RolloutSpec(steer="pure_pursuit", accel="pid", model="dynamic", max_steps=g["steps"],
+                                    replan_horizon=g["horizon"], replan_stride=g["stride"], replan_after=3)
+            ref = loop.rollout_episode(loop.Track(cx, cy, curve, closed=g["closed"]), spec, p64, unhex(g["init"]))
+            k = int(bad[0])
+            assert min(ref["pp_margin"][k], ref["near_margin"][k]) < 2e-5, (k, ref["pp_margin"][k])
+            n = k
+            tr = tr[:n]
+            assert n >= 50
     # (the batched API takes fp32 parameter rows: kp = 0.35 etc. are rounded, which the audit build then integrates)
     tol = (2e-5, 2e-6) if precision == "fp64" else (1e-3, 1e-4)
     assert np.hypot(tr[:, abi.T_X] - want[:n, 0], tr[:, abi.T_Y] - want[:n, 1]).max() < tol[0]
