@@ -22,6 +22,11 @@ unmodified ``core.controllers``, ``core.data.car_state``, ``vehicle_config`` and
 the absent third-party imports, see ``oracle/ref_shim.py``) and freezes their
 outputs on seeded inputs into ``tests/golden/*.json``;  ``tests/test_oracle_golden.py``
 checks every oracle function against those vectors bit-for-bit (fp64).
+``oracle/gen_golden_shadowed.py`` does the same for the dead-code Stanley variant (executed from the reference's
+own source lines via ``ast``) and ``oracle/gen_golden_replan.py`` for the re-planning regime (the reference's
+``Planner`` and ``Controller`` NODES run unmodified around a stubbed planner library and simulator call).
+``tests/test_oracle_vs_reference_live.py`` additionally calls the reference live, on freshly drawn inputs, wherever
+the tree is mounted.
 
 Pieces whose arithmetic lives in third-party packages that are absent from
 /root/reference and from this image are "parity unpinned" and say so where they
@@ -32,6 +37,6 @@ are defined:
                           dynamics definition (core/controllers.py:511-548) is restated.
 ORACLE-DEFINED extensions (no reference code exists): the kinematic
 bicycle step, per-step error logging for non-Stanley laws, cone hits, the
-lap-completion rule for closed tracks, observation noise.  Each is documented in
-``oracle/loop.py``.
+lap-completion rule for closed tracks, observation noise, and the window planner that stands in for
+fsd-path-planning in the re-planning regime.  Each is documented in ``oracle/loop.py``.
 """
