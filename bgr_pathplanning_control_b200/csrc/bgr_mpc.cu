@@ -162,6 +162,7 @@ struct CandStats {   // per candidate: statistics of the prefix sums of its cont
   double SA;         // sum_{k=0..H} A_k                   A_k = dt * sum_{i<k} accel_i   (v_k = v0 + A_k, :526)
   double vreq;       // -min_{k=1..H} A_k : feasible (v_k >= 0 for all k, :536) iff v0 >= vreq
 };
+constexpr double kMpcSane = 1e100;   // statistics / coefficients beyond this are treated as non-finite
 struct EpiCoef {     // per episode
   double C0, C1, C2, C3, v0;
 };
@@ -187,6 +188,13 @@ __device__ __forceinline__ void candidate_stats(const float* __restrict__ bank, 
   r.G = U + q3 * SA2;
   r.SS = SS; r.SS2 = SS2; r.SA = SA;
   r.vreq = -Amin;
+  // A candidate with a non-finite (or absurdly large) statistic can never be selected: it is made infeasible here,
+  // once, so that the pair loop of the evaluator needs no NaN test (and cannot overflow)
+  if (!(fabs(r.G) < kMpcSane && fabs(SS) < kMpcSane && fabs(SS2) < kMpcSane && fabs(SA) < kMpcSane &&
+        fabs(r.vreq) < kMpcSane)) {
+    r.G = r.SS = r.SS2 = r.SA = 0.0;
+    r.vreq = __longlong_as_double(0x7ff0000000000000LL);          // +inf: v0 >= vreq is false for every episode
+  }
   out[c] = r;
 }
 
@@ -229,6 +237,11 @@ __device__ __forceinline__ void episode_coef(const MpcArgs& A, EpiCoef* __restri
   r.C2 = A.q2 * cyw * cyw;
   r.C3 = 2.0 * A.q3 * ev0;
   r.v0 = v0;
+  if (!(fabs(r.C0) < kMpcSane && fabs(r.C1) < kMpcSane && fabs(r.C2) < kMpcSane && fabs(r.C3) < kMpcSane &&
+        fabs(v0) < kMpcSane)) {      // non-finite state: no candidate is feasible (the solver-failure fallback)
+    r.C0 = r.C1 = r.C2 = r.C3 = 0.0;
+    r.v0 = __longlong_as_double(0xfff0000000000000LL);            // -inf
+  }
   out[e] = r;
 }
 
@@ -296,9 +309,8 @@ __global__ void __launch_bounds__(kFactThreads) mpc_factored_kernel(const CandSt
     for (int r = 0; r < kFactPerLane; ++r) {
       // two independent FMA pairs (shorter dependency chain than a 4-deep Horner form)
       const double J = fma(ec[r].C1, cs.SS, ec[r].C0 + cs.G) + fma(ec[r].C3, cs.SA, ec[r].C2 * cs.SS2);
-      float costf = static_cast<float>(J);
-      if (!(ec[r].v0 >= cs.vreq) || !(costf == costf)) costf = INFINITY;         // infeasible (:536) / NaN
-      costf = fmaxf(costf, 0.0f);                                               // round-off below an exact zero
+      // (J is finite: non-finite inputs were made infeasible by the prepare kernel)   infeasible: :536
+      const float costf = ec[r].v0 >= cs.vreq ? fmaxf(static_cast<float>(J), 0.0f) : INFINITY;   // 0: round-off below an exact zero
       if (costs != nullptr) {
         const long long e = e_first + 32 * r;
         if (e < n_episodes) costs[static_cast<size_t>(e) * K + c0 + c] = costf;

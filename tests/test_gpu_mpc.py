@@ -129,3 +129,26 @@ def test_factored_evaluator_equals_explicit_rollout(cuda_device):
     np.testing.assert_allclose(expl.costs[fin], audit.costs[fin], rtol=2e-5)      # fp32 accumulation over 31 stages
     assert (fact.best_idx == audit.best_idx).mean() > 0.99
     assert np.array_equal(fact.best_cost, fact.costs[np.arange(E), fact.best_idx])
+
+
+def test_non_finite_inputs_are_infeasible_not_selected(cuda_device):
+    """A NaN / inf episode state has no feasible candidate (index -1, the solver-failure fallback :558-562); a candidate
+    with a non-finite control is never selected and costs +inf for everybody.  (The evaluator's pair loop carries no
+    NaN test: non-finite inputs are neutralised once, by the prepare kernel.)"""
+    ta = bgr.tracks.stadium_oval(256)
+    track = bgr.Track.from_arrays(ta)
+    H, K, E = 10, 64, 6
+    states, ref_start = bgr.sweeps.mpc_states(ta, E)
+    states[1, 0] = np.nan
+    states[2, 3] = np.inf
+    states[3, 2] = -np.inf
+    bank = bgr.candidate_bank(K, H)
+    bank[5, 3, 1] = np.nan
+    bank[9, 0, 0] = np.inf
+    res = bgr.mpc_evaluate(track, bgr.MpcConfig(horizon=H), states, ref_start, bank, return_costs=True)
+    assert list(res.best_idx[1:4]) == [-1, -1, -1] and np.all(np.isinf(res.costs[1:4]))
+    assert np.all(res.best_u[1:4] == 0.0)
+    ok = [0, 4, 5]
+    assert np.all(np.isinf(res.costs[ok][:, [5, 9]])) and np.all(res.best_idx[ok] >= 0)
+    assert not np.any(np.isin(res.best_idx[ok], [5, 9])) and np.all(np.isfinite(res.best_cost[ok]))
+    assert not np.any(np.isnan(res.costs))
