@@ -639,13 +639,13 @@ def run_mpc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, barrier):
             roof = {"bound": "fp32", "achieved": ach, "peak": fp32_tflops, "unit": "TFLOP/s", "frac": ach / fp32_tflops,
                     "traffic": None, "kernel_ms_last": kernel_ms}
         else:
-            # factored evaluator: 4 fp64 FMAs + 1 add per (episode, candidate) pair = 9 flops on the FP64 CUDA-core
+            # factored evaluator: 3 fp64 FMAs + 1 add per (episode, candidate) pair = 7 flops on the FP64 CUDA-core
             # pipe (64 FMA lanes per SM); nominal peak = 148 SMs x 64 x 2 x 1.965 GHz
-            ach = float(E) * K * 9.0 / (kernel_ms * 1e-3) / 1e12
+            ach = float(E) * K * 7.0 / (kernel_ms * 1e-3) / 1e12
             peak64 = 148 * 64 * 2 * 1.965e9 / 1e12
             roof = {"bound": "fp64", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64,
                     "traffic": None, "kernel_ms_last": kernel_ms, "peak_source": "nominal 148 SM x 64 lanes x 2 x 1.965 GHz",
-                    "note": "the explicit 30-stage rollout needs 29 flops per candidate-step; the factored form needs 9 per "
+                    "note": "the explicit 30-stage rollout needs 29 flops per candidate-step; the factored form needs 7 per "
                             "PAIR -- candidate-steps/s is the BASELINE metric, this roofline is of the kernel that runs"}
         print(json.dumps({
             "metric": "MPC candidate-steps/sec (episodes x candidates x horizon)", "value": units / (ms * 1e-3),
@@ -655,7 +655,7 @@ def run_mpc(args, bgr, abi, rf, torch, dist, rank, world, local, dev, barrier):
             "config": {"workload": "config 4: MPC candidate-sequence rollout/cost evaluation, 16384 episodes x 4096 "
                                    "candidates x horizon 30", "solves_per_s": E * world * args.steps / (ms * 1e-3),
                        "evaluator": "explicit fp32 stage rollout" if cfg.explicit_rollout else
-                       "factored (prefix-sum statistics, 4 fp64 FMAs per episode-candidate pair)",
+                       "factored (prefix-sum statistics, 3 fp64 FMAs + 1 add per episode-candidate pair)",
                        "launch": launch_mode},
             "e2e": {"value": float(E) * K * H * args.steps / e2e_s, "unit": "candidate-steps/s",
                     "h2d_bytes_per_step": states.nbytes + ref_start.nbytes + bank.nbytes, "d2h_bytes_per_step": E * 16},

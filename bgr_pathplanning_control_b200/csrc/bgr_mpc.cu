@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(kFactThreads) mpc_factored_kernel(const CandSt
     const CandStats cs = s_c[c];
 #pragma unroll
     for (int r = 0; r < kFactPerLane; ++r) {
-      // two independent FMA pairs (shorter dependency chain than a 4-deep Horner form)
-      const double J = fma(ec[r].C1, cs.SS, ec[r].C0 + cs.G) + fma(ec[r].C3, cs.SA, ec[r].C2 * cs.SS2);
+      // three FMAs and one add (the four episodes of a lane are independent chains: depth does not matter, count does)
+      const double J = fma(ec[r].C3, cs.SA, fma(ec[r].C2, cs.SS2, fma(ec[r].C1, cs.SS, cs.G))) + ec[r].C0;
       // (J is finite: non-finite inputs were made infeasible by the prepare kernel)   infeasible: :536
       const float costf = ec[r].v0 >= cs.vreq ? fmaxf(static_cast<float>(J), 0.0f) : INFINITY;   // 0: round-off below an exact zero
       if (costs != nullptr) {
