@@ -39,7 +39,7 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("workload", ["pp_sweep", "stanley_lqg", "mpc", "skidpad_mc"])
+@pytest.mark.parametrize("workload", ["pp_sweep", "stanley_lqg", "mpc", "skidpad_mc", "pp_replan"])
 def test_gpu_arm_json_line(workload):
     d = run_bench("--workload", workload, "--steps", "3", "--warmup", "3", "--episodes", "16384", "--sim-steps", "300",
                   "--cpu-seconds", "1")
