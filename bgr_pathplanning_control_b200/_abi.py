@@ -11,11 +11,13 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbgr_rollout.so")
+# BGR_ROLLOUT_LIB: an A/B build of the SAME library with a different compile-time knob (csrc/Makefile VARIANT=...);
+# a measurement aid for kernel work, not a second backend -- every build is sm_100a CUDA behind the same ABI
+LIB_PATH = os.environ.get("BGR_ROLLOUT_LIB") or os.path.join(HERE, "libbgr_rollout.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "bgr_rollout.h")
 
 # ---- constants restated from include/bgr_rollout.h (tests/test_abi.py checks them against the header) ----
-BGR_ABI_VERSION = 2
+BGR_ABI_VERSION = 3
 BGR_OK, BGR_ERR_BAD_ARG, BGR_ERR_CUDA, BGR_ERR_TOO_LARGE, BGR_ERR_ALLOC, BGR_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 STEER_PURE_PURSUIT, STEER_STANLEY = 0, 1
 ACCEL_PID, ACCEL_LQG = 0, 1
@@ -88,7 +90,7 @@ class RolloutCfg(C.Structure):
                 ("episode_id_base", C.c_int64), ("stanley_max_steer_rate", C.c_double),
                 ("stanley_alpha", C.c_double),
                 ("replan_horizon", C.c_int32), ("replan_stride", C.c_int32), ("replan_after", C.c_int32),
-                ("reserved2", C.c_int32), ("planner_lookahead", C.c_double)]
+                ("reserved2", C.c_int32), ("planner_lookahead", C.c_double), ("stanley_lookahead", C.c_double)]
 
 
 class MpcCfg(C.Structure):

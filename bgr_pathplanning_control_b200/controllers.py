@@ -130,8 +130,6 @@ class ShadowedStanleyController:
 
     def __init__(self, k=conf.k_stanley, k_soft=conf.k_soft_stanley, max_steer_rate=np.deg2rad(30), alpha=0.5,
                  lookahead_distance=0.0):
-        if lookahead_distance > 0:
-            raise NotImplementedError("the optional look-ahead advance (:276-281) is not built; the default is 0.0")
         self.k, self.k_soft = k, k_soft
         self.max_steer_rate, self.alpha = max_steer_rate, alpha
         self.lookahead_distance = lookahead_distance
@@ -143,7 +141,8 @@ class ShadowedStanleyController:
         params = engine.default_params(1, np.float64)
         params[0, abi.P_K_STANLEY], params[0, abi.P_K_SOFT] = self.k, self.k_soft
         cfg = engine.RolloutConfig(steer="stanley", precision="fp64", dt=dt, stanley_shadowed=True,
-                                   stanley_max_steer_rate=self.max_steer_rate, stanley_alpha=self.alpha)
+                                   stanley_max_steer_rate=self.max_steer_rate, stanley_alpha=self.alpha,
+                                   stanley_lookahead=max(0.0, float(self.lookahead_distance)))     # :276-281
         ctrl = np.zeros((1, abi.N_CTRL))
         ctrl[0, abi.C_PREV_STEER] = self.previous_steering
         out, ti = _step(track, cfg, abi.PHASE_STEER | abi.PHASE_ERRORS, params, _state_row(state), 0, ctrl,

@@ -4,6 +4,7 @@
 // entry point returns BGR_ERR_CUDA.
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -546,7 +547,7 @@ struct StepPlumbing {
   bool force_full = false;
 };
 
-using LaunchFn = cudaError_t (*)(const RolloutArgs&, int, size_t, cudaStream_t);
+using LaunchFn = cudaError_t (*)(const RolloutArgs&, int, size_t, int, cudaStream_t);
 
 template <typename Real, bool EXTRAS>
 LaunchFn pick(int s, int a, int m) {
@@ -577,7 +578,8 @@ int validate_cfg(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const c
   if (cfg->max_steps < 1 || cfg->laps < 1 || cfg->laps_target < 0 || !(cfg->dt > 0.0) || !(cfg->wheelbase > 0.0) ||
       !(cfg->max_steer > 0.0) || !(cfg->max_accel >= cfg->max_decel) || cfg->hit_radius < 0.0 ||
       cfg->tie_eps < 0.0 || cfg->sigma_xy < 0.0 || cfg->sigma_yaw < 0.0 || cfg->sigma_v < 0.0 ||
-      cfg->sigma_cone < 0.0 || cfg->stanley_max_steer_rate < 0.0 || cfg->stanley_alpha < 0.0 || cfg->stanley_alpha > 1.0) {
+      cfg->sigma_cone < 0.0 || cfg->stanley_max_steer_rate < 0.0 || cfg->stanley_alpha < 0.0 || cfg->stanley_alpha > 1.0 ||
+      !(cfg->stanley_lookahead >= 0.0)) {
     set_error("%s: invalid cfg (max_steps %d, laps %d, laps_target %d, dt %g, wheelbase %g, max_steer %g, ...)",
               who, cfg->max_steps, cfg->laps, cfg->laps_target, cfg->dt, cfg->wheelbase, cfg->max_steer);
     return BGR_ERR_BAD_ARG;
@@ -611,6 +613,7 @@ struct Plan {
   RolloutArgs A;
   LaunchFn fn = nullptr;
   size_t smem = 0;
+  int smem_optin = 0;   // the device's opt-in shared-memory maximum (per-function attribute of every step kernel)
 };
 
 // Validate the configuration, fill the kernel arguments that do not depend on the episode range, pick the kernel
@@ -623,6 +626,7 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   rc = device_info(track->device, &di);
   if (rc != BGR_OK) return rc;
 
+  plan->smem_optin = di.max_smem_optin;
   const bool f64 = cfg->precision == BGR_PRECISION_FP64;
   const bool cones_on = cfg->hit_radius > 0.0 && track->n_cones > 0;
   const bool noise_on = cfg->sigma_xy > 0.0 || cfg->sigma_yaw > 0.0 || cfg->sigma_v > 0.0;
@@ -656,7 +660,9 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   A.max_steps = cfg->max_steps;
   A.laps = cfg->laps;
   A.laps_target = cfg->laps_target;
+  A.lap_stop = cfg->laps_target > 0 ? cfg->laps_target : INT32_MAX;
   A.n_total = cfg->steer_kind == BGR_STEER_PURE_PURSUIT ? track->n * cfg->laps : track->n;
+  A.ti_chunk_max = track->n >= 8 ? A.n_total - 4 : INT32_MIN;
   A.dt = cfg->dt;
   A.wheelbase = cfg->wheelbase;
   A.l_f = cfg->l_f;
@@ -674,6 +680,7 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   A.sigma_v = cfg->sigma_v;
   A.sigma_cone = cfg->sigma_cone;
   A.f.dt = static_cast<float>(cfg->dt);
+  A.f.dt_lo = static_cast<float>(cfg->dt - static_cast<double>(static_cast<float>(cfg->dt)));
   A.f.inv_dt = static_cast<float>(1.0 / cfg->dt);
   A.f.WB = static_cast<float>(cfg->wheelbase);
   A.f.inv_WB = static_cast<float>(1.0 / cfg->wheelbase);
@@ -694,6 +701,8 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   A.st_alpha = cfg->stanley_alpha > 0.0 ? cfg->stanley_alpha : 0.5;
   A.f.st_max_delta = static_cast<float>(A.st_rate * cfg->dt);
   A.f.st_alpha = static_cast<float>(A.st_alpha);
+  A.st_lookahead = shadowed ? cfg->stanley_lookahead : 0.0;
+  A.f.st_lookahead = static_cast<float>(A.st_lookahead);
   A.replan_M = replan ? cfg->replan_horizon : 0;
   A.replan_q = cfg->replan_stride > 0 ? cfg->replan_stride : 1;
   A.replan_after = cfg->replan_after;
@@ -776,7 +785,7 @@ int launch_range(const Plan& plan, long long id_offset, long long count, const f
   A.idx = d_idx;
   A.count = d_count;
   const int grid = static_cast<int>((count + kRolloutThreads - 1) / kRolloutThreads);
-  cudaError_t err = plan.fn(A, grid, plan.smem, stream);
+  cudaError_t err = plan.fn(A, grid, plan.smem, plan.smem_optin, stream);
   if (err == cudaSuccess) count_launch();
   return check_cuda(err, "rollout kernel launch");
 }

@@ -40,7 +40,8 @@ struct RT<double> {
 };
 
 // Device view of a track handle.  Per-waypoint tables: the base lap followed by a cyclic pad (entry j >= n
-// replicates entry j - n) so that unrolled forward scans need no index wrap; n_pad = n + 8 rounded up to 4:
+// replicates entry j - n) so that unrolled forward scans need no index wrap; n_pad = n + 12 rounded up to 4 (the
+// fp32 xy table also carries 4 cyclic entries IN FRONT of waypoint 0: entry t holds waypoint t - 4):
 //   xy    : (x, y)                                 nodes/planner.py:88
 //   attr  : (kappa, path_yaw, sin path_yaw, cos path_yaw)   nodes/planner.py:89, core/controllers.py:361-368
 //   guard2: squared exactness-guard radius of the local nearest search
@@ -69,7 +70,9 @@ struct RolloutF32 {
   float dt, inv_dt, WB, inv_WB, l_f, l_r, max_steer, tan_max_steer, max_accel, max_decel;
   float tie_eps, hit_radius, K0, K1, sigma_xy, sigma_yaw, sigma_v, sigma_cone;
   float st_max_delta, st_alpha;   // shadowed Stanley: max_steer_rate * dt, alpha
+  float st_lookahead;             // shadowed Stanley: optional look-ahead advance (core/controllers.py:276-281); 0 = off
   float plan_Lf;                  // re-planning replay: the planner's own look-ahead distance
+  float dt_lo;                    // dt - float(dt): the double-float integrators advance by dt_hi + dt_lo
 };
 
 struct RolloutArgs {
@@ -92,13 +95,17 @@ struct RolloutArgs {
   int32_t traj_stride;    // rows per episode in the trajectory dump (the configured step count, also in a capped phase)
   int32_t laps;
   int32_t laps_target;
+  int32_t lap_stop;       // laps_target, or INT_MAX when the lap rule is off (one compare in the step kernels)
   int32_t n_total;  // PP: n * laps; Stanley: n
+  int32_t ti_chunk_max;  // fp32 kernels: last target index from which a 3-waypoint chunk may start (n_total - 4;
+                         // INT_MIN on tracks of fewer than 8 waypoints, whose scans run one waypoint at a time)
   double dt, wheelbase, l_f, l_r, max_steer, max_accel, max_decel;
   double hit_radius, tie_eps;
   double lqr_k0, lqr_k1;
   double inv_dt, inv_wheelbase, tan_max_steer;  // host-computed loop invariants of the fp32 kernels
   double sigma_xy, sigma_yaw, sigma_v, sigma_cone;
   double st_rate, st_alpha;   // shadowed Stanley variant (core/controllers.py:234-324)
+  double st_lookahead;        // ... its optional look-ahead advance (:276-281); 0 = off
   int32_t stanley_shadowed;
   // receding-horizon re-planning replay (nodes/planner.py:26,62,72-77); replan_M = 0: off
   int32_t replan_M, replan_q, replan_after;

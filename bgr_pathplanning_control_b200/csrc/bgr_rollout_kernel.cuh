@@ -348,10 +348,26 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
       } else {
         // live Stanley law (core/controllers.py:336-385)
         j_obs = nearest(oxl, oyl, near);
-        Real e_ct, theta_e;
-        errors_at(j_obs, oxl, oyl, oyaw, e_ct, theta_e);
         bool shadowed = false;
         if constexpr (EXTRAS) shadowed = A.stanley_shadowed != 0;
+        int j_law = j_obs;
+        if constexpr (EXTRAS) {
+          if (shadowed && A.st_lookahead > 0.0) {
+            // optional look-ahead advance of the shadowed variant (core/controllers.py:276-281): from the nearest
+            // waypoint, forward while it is closer than lookahead_distance and below the last index
+            const Real la = static_cast<Real>(A.st_lookahead);
+            const Real la_metric = kF64 ? la : la * la;
+            const Real tie_la = kF64 ? tie_eps : tie_eps * (Real(2) * la + tie_eps);
+            while (j_law < n - 1) {                                  // :277
+              const Real d = dist(j_law, oxl, oyl);                  // :278
+              tie_now |= fabs(d - la_metric) <= tie_la;
+              if (d >= la_metric) break;                             // :279
+              ++j_law;                                               // :281
+            }
+          }
+        }
+        Real e_ct, theta_e;
+        errors_at(j_law, oxl, oyl, oyaw, e_ct, theta_e);
         if (shadowed) {
           // the SHADOWED class body (core/controllers.py:305-322): adaptive gain, rate limit, low-pass filter
           const Real adaptive_k = k_st / (ov + k_soft);              // :305
@@ -368,8 +384,8 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
           delta = normalize_angle(delta);                            // :380
           delta = clampr(delta, -max_steer, max_steer);              // :381
         }
-        ti = j_obs;
-        tim = j_obs;
+        ti = j_law;                                                  // the law returns the index it used (:324 / :385)
+        tim = j_law;
       }
 
       // ---- 3. curvature lookup (nodes/controller.py:62) ----
@@ -621,10 +637,11 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
 #define BGR_DEFINE_LAUNCH(Real, STEER, ACCEL, MODEL, EXTRAS)                                              \
   template <>                                                                                            \
   cudaError_t launch_rollout<Real, STEER, ACCEL, MODEL, EXTRAS>(const RolloutArgs& args, int grid,        \
-                                                                 size_t smem, cudaStream_t stream) {     \
+                                                                 size_t smem, int smem_optin,            \
+                                                                 cudaStream_t stream) {                  \
     auto kern = rollout_kernel<Real, STEER, ACCEL, MODEL, EXTRAS>;                                        \
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                           static_cast<int>(smem));                                      \
+    /* per-function attribute: always the device's opt-in maximum, so concurrent callers cannot lower it */ \
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin); \
     if (err != cudaSuccess) return err;                                                                  \
     kern<<<grid, kRolloutThreads, smem, stream>>>(args);                                                 \
     return cudaGetLastError();                                                                           \

@@ -134,6 +134,7 @@ class RolloutConfig:
     stanley_shadowed: bool = False   # the dead-code Stanley variant (core/controllers.py:234-324); labelled extra
     stanley_max_steer_rate: float = 0.0   # 0 = reference default deg2rad(30) rad/s
     stanley_alpha: float = 0.0            # 0 = reference default 0.5
+    stanley_lookahead: float = 0.0        # shadowed variant's optional look-ahead advance (:276-281); 0 = off
     # receding-horizon re-planning replay (nodes/planner.py:26,62,72-77; pure pursuit only): the controller sees a
     # local path of `replan_horizon` points (every `replan_stride`-th centreline waypoint from the one nearest to the
     # car), re-planned whenever the planner's own look-ahead index has passed `replan_after`.  0 = off.
@@ -152,6 +153,7 @@ class RolloutConfig:
         c.max_steps, c.laps, c.laps_target = int(self.max_steps), int(self.laps), int(self.laps_target)
         c.flags = (abi.CFG_AUDIT if self.audit else 0) | (abi.CFG_STANLEY_SHADOWED if self.stanley_shadowed else 0)
         c.stanley_max_steer_rate, c.stanley_alpha = float(self.stanley_max_steer_rate), float(self.stanley_alpha)
+        c.stanley_lookahead = float(self.stanley_lookahead)
         for k in ("dt", "wheelbase", "l_f", "l_r", "max_steer", "max_accel", "max_decel", "hit_radius", "tie_eps",
                   "sigma_xy", "sigma_yaw", "sigma_v", "sigma_cone"):
             setattr(c, k, float(getattr(self, k)))

@@ -15,7 +15,14 @@ def pp_sweep_params(n_episodes=1 << 20, start=0):
     """Config 2: pure-pursuit look-ahead / PID-gain grid.  Lf in linspace(2, 9, 64) x kp in
     linspace(0.1, 1, 32) x ki in linspace(0, 0.8, 16) x kd in linspace(0, 0.6, 32) = 1 048 576 combos,
     kd fastest.  Rows ``start .. start + n_episodes`` of the flattened grid (wrapping)."""
-    idx = (np.arange(n_episodes, dtype=np.int64) + start) % (64 * 32 * 16 * 32)
+    return pp_sweep_rows(np.arange(n_episodes, dtype=np.int64) + start)
+
+
+def pp_sweep_rows(rows):
+    """Rows ``rows`` (any integer array, wrapping) of the flattened config-2 grid: parameter row i is
+    (Lf[i // 16384], kp[(i // 512) % 32], ki[(i // 32) % 16], kd[i % 32])."""
+    idx = np.asarray(rows, dtype=np.int64) % (64 * 32 * 16 * 32)
+    n_episodes = len(idx)
     i_kd = idx % 32
     i_ki = (idx // 32) % 16
     i_kp = (idx // (32 * 16)) % 32
@@ -39,6 +46,18 @@ def stanley_lqg_params(n_episodes=1 << 22, seed=20261019, start=0):
     p[:, abi.P_C_F] = conf.c_f * (0.8 + 0.4 * u[:, 3])
     p[:, abi.P_C_R] = conf.c_r * (0.8 + 0.4 * u[:, 4])
     return p.astype(np.float32)
+
+
+def stanley_lqg_rows(rows, seed=20261019):
+    """Config 3's parameter rows at arbitrary absolute row numbers (a stratified sample of the 4 Mi sweep)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    out = np.empty((len(rows), abi.N_PARAMS), dtype=np.float32)
+    B = 1 << 16
+    for b in np.unique(rows // B):
+        sel = np.nonzero(rows // B == b)[0]
+        blk = stanley_lqg_params(B, seed=seed, start=int(b) * B)
+        out[sel] = blk[rows[sel] - int(b) * B]
+    return out
 
 
 def _uniform_rows(seed, start, n, cols):

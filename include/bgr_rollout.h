@@ -34,7 +34,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden: only this ABI is exported */
 #endif
 
-#define BGR_ABI_VERSION 2
+#define BGR_ABI_VERSION 3
 
 /* ---- status codes ---- */
 #define BGR_OK 0
@@ -212,6 +212,10 @@ typedef struct bgr_rollout_cfg {
   int32_t replan_after;     /* re-plan when the planner's index > this; reference value 3 (nodes/planner.py:26) */
   int32_t reserved2;
   double planner_lookahead; /* the planner's own look-ahead (nodes/planner.py:75); 0 = 5.5 (vehicle_config.py:37) */
+  /* BGR_CFG_STANLEY_SHADOWED only: the optional look-ahead advance of the dead-code variant (core/controllers.py:
+   * 276-281) -- from the nearest waypoint the index moves forward while it is closer than this distance and below
+   * n - 1; the error terms of the law are taken there.  0 = off (the constructor default, :234). */
+  double stanley_lookahead;
 } bgr_rollout_cfg_t;
 
 #define BGR_MPC_EXPLICIT_ROLLOUT 1 /* bgr_mpc_cfg_t.flags: score candidates by the explicit stage-by-stage rollout

@@ -75,6 +75,26 @@ def main():
         rows.append({"state": hx([x, y, yaw, v]), "k": hx(k), "k_soft": hx(ks), "rate": hx(rate), "alpha": hx(alpha),
                      "prev": hx(prev), "dt": hx(dt), "steering": hx(s), "ind": int(ind), "prev_out": hx(c.previous_steering)})
     G["single"] = rows
+    # the optional look-ahead advance (:276-281): a separate generator stream, so the rows above stay what they were
+    rng2 = np.random.default_rng(2403)
+    rows = []
+    for _ in range(96):
+        i = int(rng2.integers(0, 720))
+        x, y = cx[i] + rng2.normal(0, 0.6), cy[i] + rng2.normal(0, 0.6)
+        yaw = math.atan2(20.0 * math.cos(th[i]), -40.0 * math.sin(th[i])) + rng2.normal(0, 0.4)
+        v = float(rng2.uniform(0.0, 10.0))
+        k, ks = float(rng2.uniform(0.2, 2.0)), float(rng2.uniform(0.01, 1.0))
+        prev, dt = float(rng2.uniform(-0.5, 0.5)), float(rng2.choice([0.05, 0.1]))
+        la = float(rng2.uniform(0.3, 6.0))
+        c = Shadowed(k=k, k_soft=ks, lookahead_distance=la)
+        c.previous_steering = prev
+        # the last third runs on an OPEN path that ends shortly after the car: the advance stops at len(cx) - 1 (:277)
+        pth = path if len(rows) < 64 else path[: min(720, i + 6)]
+        s, ind = c.compute_steering(CS.State(x=x, y=y, yaw=yaw, v=v), pth, 0, dt)
+        rows.append({"state": hx([x, y, yaw, v]), "k": hx(k), "k_soft": hx(ks), "prev": hx(prev), "dt": hx(dt),
+                     "lookahead": hx(la), "n_path": len(pth), "steering": hx(s), "ind": int(ind),
+                     "prev_out": hx(c.previous_steering)})
+    G["single_lookahead"] = rows
     # closed loop: shadowed Stanley (constructor defaults) + PID + State.update, 400 periods
     ref_shim.FixedDtPID.dt = conf.dt
     curve = (40.0 * 20.0) / ((40.0 * np.sin(th)) ** 2 + (20.0 * np.cos(th)) ** 2) ** 1.5

@@ -150,7 +150,7 @@ def stanley_steering(x, y, yaw, v, cx, cy, k=1.0, k_soft=0.1, max_steer=CONF.MAX
 # limit, low-pass filter, carried ``previous_steering`` (stored BEFORE the final clip, :319-322).
 # Labelled extra (SURVEY.md section 8 row a2'); pinned by tests/golden/shadowed_stanley_kat.json, which
 # oracle/gen_golden_shadowed.py produces by executing the reference's own source for these lines.
-# ``lookahead_distance`` (:276-281) is kept at its default 0.0 (no look-ahead advance).
+# ``lookahead_distance`` (:276-281): the optional advance of the index from the nearest point (default 0.0 = off).
 # --------------------------------------------------------------------------------------
 SHADOWED_RATE = float(np.deg2rad(30))      # max_steer_rate default (:234)
 SHADOWED_ALPHA = 0.5                       # alpha default (:234)
@@ -158,9 +158,20 @@ SHADOWED_ALPHA = 0.5                       # alpha default (:234)
 
 def stanley_shadowed_steering(x, y, yaw, v, cx, cy, previous_steering, dt, k=CONF.k_stanley,
                               k_soft=CONF.k_soft_stanley, max_steer_rate=SHADOWED_RATE, alpha=SHADOWED_ALPHA,
-                              max_steer=CONF.MAX_STEER):
+                              max_steer=CONF.MAX_STEER, lookahead_distance=0.0):
     """Returns (steering, ind, new_previous_steering)."""
-    ind, theta_e, e_ct, _ = nearest_point_errors(x, y, yaw, cx, cy)             # :269-302
+    ind, theta_e, e_ct, _ = nearest_point_errors(x, y, yaw, cx, cy)             # :269-273, :283-302
+    if lookahead_distance > 0:                                                   # :276
+        while ind < len(cx) - 1:                                                 # :277
+            distance = np.hypot(cx[ind] - x, cy[ind] - y)                        # :278
+            if distance >= lookahead_distance:                                   # :279
+                break
+            ind += 1                                                             # :281
+        path_yaw = path_heading(cx, cy, ind)                                     # :286-294
+        theta_e = float(normalize_angle(path_yaw - yaw))                         # :297
+        ddx = cx[ind] - x                                                        # :300
+        ddy = cy[ind] - y                                                        # :301
+        e_ct = float(-ddx * np.sin(path_yaw) + ddy * np.cos(path_yaw))           # :302
     adaptive_k = k / (v + k_soft)                                                # :305
     steering = theta_e + math.atan2(adaptive_k * e_ct, 1.0)                      # :308
     steering = normalize_angle(steering)                                         # :309

@@ -81,6 +81,7 @@ class RolloutSpec:
     steer: str = "pure_pursuit"       # "pure_pursuit" | "stanley" | "stanley_shadowed" (dead-code variant, :234-324)
     shadowed_rate: float = laws.SHADOWED_RATE
     shadowed_alpha: float = laws.SHADOWED_ALPHA
+    shadowed_lookahead: float = 0.0   # the variant's optional look-ahead advance (:276-281)
     accel: str = "pid"                # "pid" | "lqg"
     model: str = "kinematic"          # "kinematic" | "dynamic"
     max_steps: int = 2000
@@ -226,7 +227,7 @@ def rollout_episode(track: Track, spec: RolloutSpec, params, init_state, episode
         elif spec.steer == "stanley_shadowed":
             delta, ti, prev_steer = laws.stanley_shadowed_steering(
                 ox, oy, oyaw, ov, cx_lap, cy_lap, prev_steer, dt, p[P_K_STANLEY], p[P_K_SOFT],
-                spec.shadowed_rate, spec.shadowed_alpha, conf.MAX_STEER)
+                spec.shadowed_rate, spec.shadowed_alpha, conf.MAX_STEER, spec.shadowed_lookahead)
         else:
             raise ValueError(spec.steer)
         # 3. curvature lookup (nodes/controller.py:62)

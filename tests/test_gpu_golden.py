@@ -293,8 +293,37 @@ def test_shadowed_stanley_variant(cuda_device):
         s, ind = ctl.compute_steering(Obj(x=x, y=y, yaw=yaw, v=v), path, 0, unhex(row["dt"]))
         assert int(ind) == row["ind"]
         assert close(s, unhex(row["steering"]), atol=1e-13) and close(ctl.previous_steering, unhex(row["prev_out"]), atol=1e-13)
-    with pytest.raises(NotImplementedError):
-        bgr.ShadowedStanleyController(lookahead_distance=2.0)
+    # the optional look-ahead advance (:276-281): closed ellipse and open paths that end just ahead of the car
+    advanced = 0
+    for row in g["single_lookahead"]:
+        x, y, yaw, v = unhex(row["state"])
+        n = row["n_path"]
+        ctl = bgr.ShadowedStanleyController(k=unhex(row["k"]), k_soft=unhex(row["k_soft"]),
+                                            lookahead_distance=unhex(row["lookahead"]))
+        ctl.previous_steering = unhex(row["prev"])
+        s, ind = ctl.compute_steering(Obj(x=x, y=y, yaw=yaw, v=v), path[:n], 0, unhex(row["dt"]))
+        assert int(ind) == row["ind"], row
+        assert close(s, unhex(row["steering"]), atol=1e-13) and close(ctl.previous_steering, unhex(row["prev_out"]), atol=1e-13)
+        plain = bgr.ShadowedStanleyController(k=unhex(row["k"]), k_soft=unhex(row["k_soft"]))
+        advanced += int(plain.compute_steering(Obj(x=x, y=y, yaw=yaw, v=v), path[:n], 0, unhex(row["dt"]))[1] != row["ind"])
+    assert advanced >= 48          # the vectors do exercise the advance
+    # ... and the same advance inside a rollout: fp64 and fp32 builds against the oracle loop
+    from oracle import loop
+    ta = bgr.tracks.stadium_oval(256)
+    trk = bgr.Track.from_arrays(ta)
+    p1 = bgr.default_params(1)
+    i1 = bgr.initial_states(ta, 1, lateral_offset=[0.2], v0=4.0)
+    ref = loop.rollout_episode(loop.Track(ta.x, ta.y, ta.kappa, True, ta.cones),
+                               loop.RolloutSpec(steer="stanley_shadowed", accel="pid", model="kinematic", max_steps=300,
+                                                shadowed_lookahead=2.5), p1[0].astype(np.float64), i1[0])
+    for precision, pos_tol in (("fp64", 1e-9), ("fp32", 1e-3)):
+        cfg = bgr.RolloutConfig(steer="stanley", accel="pid", model="kinematic", precision=precision, max_steps=300,
+                                stanley_shadowed=True, stanley_lookahead=2.5)
+        tr = bgr.rollout(trk, cfg, p1, i1, traj=True).traj[0]
+        assert np.array_equal(tr[:, abi.T_TARGET_IND].astype(int), ref["ti"]), precision
+        assert np.array_equal(tr[:, abi.T_NEAREST_IND].astype(int), ref["near"]), precision
+        assert np.hypot(tr[:, abi.T_X] - ref["traj"][:, 0], tr[:, abi.T_Y] - ref["traj"][:, 1]).max() < pos_tol
+        assert np.abs(tr[:, abi.T_E_CT] - ref["e_ct"]).max() < max(pos_tol, 1e-9)
     _, _, curve = golden_loop_track()
     L = g["loop"]
     want = np.asarray(unhex(L["traj"]))

@@ -247,6 +247,16 @@ def test_shadowed_stanley_variant():
                                                       unhex(row["alpha"]))
         assert ind == row["ind"]
         assert same(s, unhex(row["steering"])) and same(prev, unhex(row["prev_out"])), row
+    # the optional look-ahead advance (:276-281), on the closed ellipse and on open paths ending just ahead of the car
+    assert sum(r["n_path"] < 720 for r in g["single_lookahead"]) >= 16
+    for row in g["single_lookahead"]:
+        x, y, yaw, v = unhex(row["state"])
+        n = row["n_path"]
+        s, ind, prev = laws.stanley_shadowed_steering(x, y, yaw, v, cx[:n], cy[:n], unhex(row["prev"]), unhex(row["dt"]),
+                                                      unhex(row["k"]), unhex(row["k_soft"]),
+                                                      lookahead_distance=unhex(row["lookahead"]))
+        assert ind == row["ind"]
+        assert same(s, unhex(row["steering"])) and same(prev, unhex(row["prev_out"])), row
     th = np.linspace(0, 2 * np.pi, 720, endpoint=False)
     curve = (40.0 * 20.0) / ((40.0 * np.sin(th)) ** 2 + (20.0 * np.cos(th)) ** 2) ** 1.5
     L = g["loop"]
