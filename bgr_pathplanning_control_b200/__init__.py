@@ -10,8 +10,9 @@ Importing the package does not load the CUDA library; the first call does and ra
 from . import _abi, tracks, sweeps, sharding, roofline          # noqa: F401
 from .vehicle_config import Vehicle_config, conf               # noqa: F401
 from .engine import (Track, RolloutConfig, RolloutResult, MpcConfig, MpcResult, rollout, rollout_groups, mpc_evaluate,   # noqa: F401
-                     default_params, initial_states, candidate_bank, lqg_design, fp32_peak_probe,
-                     last_kernel_ms, launch_count, identify_dynamics)
+                     default_params, initial_states, candidate_bank, lqg_design, lqg_covariance, fp32_peak_probe,
+                     last_kernel_ms, launch_count, identify_dynamics, rollout_async, PendingRollout, build_id,
+                     release_group_streams, MpcBank, fp64_peak_probe)
 from .controllers import (PurePursuitController, StanleyController, ShadowedStanleyController, AccelerationPIDController,            # noqa: F401
                           LQGAccelerationController, MPCController, get_steering_controller,
                           normalize_angle, find_target_point, compute_control_commands)
@@ -19,4 +20,4 @@ from .car_state import State, States                            # noqa: F401
 from .nodes import Controller, BatchedController, SimulationLogger, path_from_planner, sim_controls   # noqa: F401
 from . import metrics_calculator                                # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -57,9 +57,13 @@ N_OUT = 8
 SYSID_COLS = 9
 
 EXPORTS = (
-    "bgr_abi_version", "bgr_last_error_string", "bgr_device_count", "bgr_track_create", "bgr_track_destroy",
-    "bgr_track_info", "bgr_track_tables", "bgr_rollout", "bgr_rollout_host", "bgr_step_host", "bgr_lqg_design",
-    "bgr_mpc_eval", "bgr_mpc_eval_host", "bgr_identify_dynamics", "bgr_identify_dynamics_host", "bgr_fp32_peak_probe", "bgr_last_kernel_ms", "bgr_launch_count",
+    "bgr_abi_version", "bgr_last_error_string", "bgr_device_count", "bgr_build_id", "bgr_stream_create", "bgr_stream_synchronize",
+    "bgr_stream_destroy",
+    "bgr_track_create", "bgr_track_destroy", "bgr_track_info", "bgr_track_tables",
+    "bgr_rollout", "bgr_rollout_host", "bgr_rollout_host_async", "bgr_step_host", "bgr_lqg_design", "bgr_lqg_covariance",
+    "bgr_mpc_eval", "bgr_mpc_eval_host", "bgr_mpc_bank_create", "bgr_mpc_bank_destroy", "bgr_mpc_eval_bank",
+    "bgr_mpc_eval_bank_host", "bgr_identify_dynamics", "bgr_identify_dynamics_host",
+    "bgr_fp32_peak_probe", "bgr_fp64_peak_probe", "bgr_last_kernel_ms", "bgr_launch_count",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -144,10 +148,32 @@ def load():
     lib.bgr_step_host.argtypes = [vp, C.POINTER(RolloutCfg), i32, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.bgr_lqg_design.restype = C.c_int
     lib.bgr_lqg_design.argtypes = [C.c_double, i32, vp, vp]
+    lib.bgr_lqg_covariance.restype = C.c_int
+    lib.bgr_lqg_covariance.argtypes = [C.c_double, i32, vp]
+    lib.bgr_build_id.restype = C.c_char_p
+    lib.bgr_build_id.argtypes = []
+    lib.bgr_stream_synchronize.restype = C.c_int
+    lib.bgr_stream_synchronize.argtypes = [vp]
+    lib.bgr_stream_create.restype = C.c_int
+    lib.bgr_stream_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.bgr_stream_destroy.restype = C.c_int
+    lib.bgr_stream_destroy.argtypes = [vp]
+    lib.bgr_rollout_host_async.restype = C.c_int
+    lib.bgr_rollout_host_async.argtypes = [vp, C.POINTER(RolloutCfg), i64, vp, vp, vp, vp, vp, vp]
     lib.bgr_mpc_eval.restype = C.c_int
     lib.bgr_mpc_eval.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.bgr_mpc_eval_host.restype = C.c_int
     lib.bgr_mpc_eval_host.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.bgr_mpc_bank_create.restype = C.c_int
+    lib.bgr_mpc_bank_create.argtypes = [C.c_int, vp, i32, i32, C.POINTER(vp)]
+    lib.bgr_mpc_bank_destroy.restype = None
+    lib.bgr_mpc_bank_destroy.argtypes = [vp]
+    lib.bgr_mpc_eval_bank.restype = C.c_int
+    lib.bgr_mpc_eval_bank.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bgr_mpc_eval_bank_host.restype = C.c_int
+    lib.bgr_mpc_eval_bank_host.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bgr_fp64_peak_probe.restype = C.c_int
+    lib.bgr_fp64_peak_probe.argtypes = [C.c_int, vp]
     lib.bgr_identify_dynamics.restype = C.c_int
     lib.bgr_identify_dynamics.argtypes = [i64, i32, vp, vp, vp, vp, vp]
     lib.bgr_identify_dynamics_host.restype = C.c_int

@@ -188,8 +188,17 @@ class LQGAccelerationController:
 
     def __init__(self, dt):
         self.dt = dt
+        # the public matrices of the reference instance (:83-94, :101-104); the gain K and every later P come from the
+        # library's own recursions (bgr_lqg_design / bgr_lqg_covariance), which also feed the kernels
+        self.A = np.array([[1, 0], [dt, 1]])                       # :83-84
+        self.B = np.array([[dt], [0]])                             # :85-86
+        self.C = np.array([[1, 0]])                                # :87
+        self.Q = np.diag([10.0, 100.0])                            # :90-92
+        self.R = np.array([[0.001]])                               # :93-94
         K, _ = engine.lqg_design(dt, 0)
         self.K = K.reshape(1, 2)                                   # :97
+        self.Q_kf = np.diag([0.1, 0.1])                            # :101-103
+        self.R_kf = np.array([[0.5]])                              # :104
         self.v_desired = 0.0
         self.a_k_prev = 0.0
         self._ctrl = np.zeros((1, abi.N_CTRL))
@@ -197,6 +206,12 @@ class LQGAccelerationController:
     @property
     def x_hat(self):
         return self._ctrl[0, abi.C_LQG_XHAT0:abi.C_LQG_XHAT1 + 1].reshape(2, 1).copy()
+
+    @property
+    def P(self):
+        """Estimate covariance (:109), advanced once per ``compute_acceleration`` call (:126, :160).  It does not depend
+        on the measurements, so it is the shared recursion evaluated at this instance's call count."""
+        return engine.lqg_covariance(self.dt, int(self._ctrl[0, abi.C_STEP]))
 
     def compute_acceleration(self, current_speed, curvature):
         params = engine.default_params(1, np.float64)
@@ -216,14 +231,18 @@ class LQGAccelerationController:
 
 class MPCController:
     """core/controllers.py:471-568 with the cvxpy/OSQP solve replaced by GPU evaluation of the same cost
-    over a bank of candidate control sequences (the optimum over the bank, not the QP optimum)."""
+    over a bank of candidate control sequences: the optimum over the bank, which for the default ``qp_family`` bank
+    lies within 0.2 % of the QP optimum in cost (tests/test_gpu_mpc.py)."""
 
-    def __init__(self, N=10, dt=0.1, n_candidates=4096, seed=20261021):
+    def __init__(self, N=10, dt=0.1, n_candidates=4096, seed=20261021, bank="qp_family"):
         self.N = N
         self.dt = dt
         self.Q = np.diag([1.0, 1.0, 0.5, 0.1])                     # :483
         self.R = np.diag([0.1, 0.1])                               # :484
-        self.bank = engine.candidate_bank(n_candidates, N, seed)
+        # default: the bank built from the QP's own separable structure -- its best candidate is within 0.2 % of the
+        # optimum OSQP converges to (engine.candidate_bank); bank="uniform" gives the generic random sample
+        self.bank = engine.candidate_bank(n_candidates, N, seed, kind=bank, dt=dt)
+        self._resident = None
         self.last_cost = None
 
     def compute_control(self, state, path):
@@ -232,7 +251,9 @@ class MPCController:
         track = _track_for(cx, cy)
         cfg = engine.MpcConfig(horizon=self.N, dt=self.dt, q=tuple(np.diag(self.Q)), r=tuple(np.diag(self.R)))
         s = np.array([[float(state.x), float(state.y), float(state.yaw), float(state.v)]])
-        res = engine.mpc_evaluate(track, cfg, s, np.zeros(1, np.int32), self.bank)
+        if self._resident is None or self._resident.device != _DEVICE:
+            self._resident = engine.MpcBank(self.bank, device=_DEVICE)      # uploaded once per controller
+        res = engine.mpc_evaluate(track, cfg, s, np.zeros(1, np.int32), self._resident)
         if int(res.best_idx[0]) < 0:
             print("MPC optimization failed. Using zero acceleration and steering.")   # :562
         self.last_cost = float(res.best_cost[0])

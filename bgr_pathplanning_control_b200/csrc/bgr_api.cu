@@ -109,7 +109,7 @@ static void lqr_gain_host(double dt, double K[2]) {
   K[1] = static_cast<double>(k1);
 }
 
-static void kalman_gains_host(double dt, int n_steps, double* out /*[n][2]*/) {
+static void kalman_gains_host(double dt, int n_steps, double* out /*[n][2] or nullptr*/, double* P_out = nullptr) {
   // A = [[1,0],[dt,1]], C = [1,0], Q_kf = 0.1 I, R_kf = 0.5, P0 = I   (:83-87, :101-109)
   double p00 = 1.0, p01 = 0.0, p10 = 0.0, p11 = 1.0;
   for (int k = 0; k < n_steps; ++k) {
@@ -124,8 +124,13 @@ static void kalman_gains_host(double dt, int n_steps, double* out /*[n][2]*/) {
     p01 = (1.0 - k0) * pp01;
     p10 = -k1 * pp00 + pp10;
     p11 = -k1 * pp01 + pp11;
-    out[2 * k] = k0;
-    out[2 * k + 1] = k1;
+    if (out != nullptr) {
+      out[2 * k] = k0;
+      out[2 * k + 1] = k1;
+    }
+  }
+  if (P_out != nullptr) {
+    P_out[0] = p00; P_out[1] = p01; P_out[2] = p10; P_out[3] = p11;
   }
 }
 
@@ -277,6 +282,47 @@ extern "C" int bgr_lqg_design(double dt, int32_t n_steps, double* h_lqr_gain, do
   }
   lqr_gain_host(dt, h_lqr_gain);
   if (h_kf_gains != nullptr && n_steps > 0) kalman_gains_host(dt, n_steps, h_kf_gains);
+  return BGR_OK;
+}
+
+extern "C" int bgr_lqg_covariance(double dt, int32_t n_steps, double* h_P) {
+  if (!(dt > 0.0) || n_steps < 0 || h_P == nullptr) {
+    set_error("bgr_lqg_covariance: need dt > 0, n_steps >= 0, h_P != NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  kalman_gains_host(dt, n_steps, nullptr, h_P);
+  return BGR_OK;
+}
+
+#ifndef BGR_BUILD_ID
+#define BGR_BUILD_ID "unknown"
+#endif
+extern "C" const char* bgr_build_id(void) { return BGR_BUILD_ID; }
+
+extern "C" int bgr_stream_synchronize(void* stream) {
+  BGR_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return BGR_OK;
+}
+
+extern "C" int bgr_stream_create(int device, void** out_stream) {
+  if (out_stream == nullptr) {
+    set_error("bgr_stream_create: out_stream is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  *out_stream = nullptr;
+  int prev = 0;
+  BGR_CUDA(cudaGetDevice(&prev));
+  BGR_CUDA(cudaSetDevice(device));
+  cudaStream_t st = nullptr;
+  const cudaError_t err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  cudaSetDevice(prev);
+  BGR_CUDA(err);
+  *out_stream = st;
+  return BGR_OK;
+}
+
+extern "C" int bgr_stream_destroy(void* stream) {
+  if (stream != nullptr) BGR_CUDA(cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
   return BGR_OK;
 }
 
@@ -986,9 +1032,34 @@ long long host_chunk() {
 
 }  // namespace
 
-extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
-                                const float* h_params, const double* h_init_state, float* h_metrics,
-                                int32_t* h_status, double* h_traj, double* h_aggregate, void* stream_) {
+namespace {
+
+// Chunk sizes of the host-buffer pipeline: full chunks in the middle, a short ramp (1/8, 1/4, 1/2 of a chunk) at both
+// ends.  The first upload and the last download of a call are the only copies nothing can hide; short end chunks make
+// them short, and their small kernels share the GPU with their neighbours on the other internal stream.
+std::vector<long long> host_chunks(long long n_episodes) {
+  const long long C = host_chunk();
+  std::vector<long long> head, tail, out;
+  long long left = n_episodes;
+  for (long long c = C / 8; c < C && left > 2 * c; c *= 2) {
+    const long long cc = std::max<long long>(kRolloutThreads, c / kRolloutThreads * kRolloutThreads);
+    head.push_back(cc);
+    tail.push_back(cc);
+    left -= 2 * cc;
+  }
+  out = head;
+  while (left > 0) {
+    const long long cc = std::min(C, left);
+    out.push_back(cc);
+    left -= cc;
+  }
+  out.insert(out.end(), tail.rbegin(), tail.rend());
+  return out;
+}
+
+int rollout_host_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
+                      const float* h_params, const double* h_init_state, float* h_metrics,
+                      int32_t* h_status, double* h_traj, double* h_aggregate, void* stream_, bool synchronous) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BGR_TRY(validate_cfg(track, cfg, "bgr_rollout_host"));
   if (n_episodes < 0) {
@@ -1055,9 +1126,8 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
   BGR_CUDA(cudaStreamWaitEvent(g_pipe.s[0], g_pipe.ready, 0));
   BGR_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ready, 0));
   int c = 0;
-  const long long chunk = host_chunk();
-  for (long long e0 = 0; e0 < n_episodes; e0 += chunk, ++c) {
-    const long long cnt = std::min<long long>(chunk, n_episodes - e0);
+  long long e0 = 0;
+  for (const long long cnt : host_chunks(n_episodes)) {
     const size_t n = static_cast<size_t>(cnt), o = static_cast<size_t>(e0);
     cudaStream_t st = g_pipe.s[c & 1];
     BGR_CUDA(cudaMemcpyAsync(d_params + o * BGR_N_PARAMS, h_params + o * BGR_N_PARAMS, n * BGR_N_PARAMS * sizeof(float),
@@ -1081,6 +1151,8 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
     if (h_traj != nullptr)
       BGR_CUDA(cudaMemcpyAsync(h_traj + o * S * BGR_N_TRAJ, d_traj + o * S * BGR_N_TRAJ,
                                n * S * BGR_N_TRAJ * sizeof(double), cudaMemcpyDeviceToHost, st));
+    e0 += cnt;
+    ++c;
   }
   for (int i = 0; i < 2; ++i) {
     BGR_CUDA(cudaEventRecord(g_pipe.done[i], g_pipe.s[i]));
@@ -1092,9 +1164,27 @@ extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_
     count_launch(2);
     BGR_CUDA(cudaMemcpyAsync(h_aggregate, d_agg, BGR_N_AGG * sizeof(double), cudaMemcpyDeviceToHost, stream));
   }
-  BGR_CUDA(cudaStreamSynchronize(stream));
-  drain.armed = false;   // the caller's stream waited on both internal streams and has been synchronised
+  // the caller's stream has waited on both internal streams: synchronising it completes the call; the scratch
+  // buffers are freed in stream order behind that wait either way
+  if (synchronous) BGR_CUDA(cudaStreamSynchronize(stream));
+  drain.armed = false;
   return BGR_OK;
+}
+
+}  // namespace
+
+extern "C" int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
+                                const float* h_params, const double* h_init_state, float* h_metrics,
+                                int32_t* h_status, double* h_traj, double* h_aggregate, void* stream) {
+  return rollout_host_impl(track, cfg, n_episodes, h_params, h_init_state, h_metrics, h_status, h_traj, h_aggregate,
+                           stream, true);
+}
+
+extern "C" int bgr_rollout_host_async(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
+                                      const float* h_params, const double* h_init_state, float* h_metrics,
+                                      int32_t* h_status, double* h_aggregate, void* stream) {
+  return rollout_host_impl(track, cfg, n_episodes, h_params, h_init_state, h_metrics, h_status, nullptr, h_aggregate,
+                           stream, false);
 }
 
 extern "C" int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg_in, int32_t phases, int64_t n,
@@ -1202,19 +1292,36 @@ static int validate_mpc(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int6
   return BGR_OK;
 }
 
-extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
-                            const double* d_state, const int32_t* d_ref_start, const int32_t* d_ref_len,
-                            const float* d_bank, int32_t n_candidates, float* d_best_u, float* d_best_cost,
-                            int32_t* d_best_idx, float* d_costs, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BGR_TRY(validate_mpc(track, cfg, n_episodes, n_candidates, "bgr_mpc_eval"));
+// Device-resident candidate bank (bgr_mpc_bank_t): the bank itself plus, per cost configuration it has been scored
+// under, the five prefix-sum statistics per candidate that the factored evaluator needs.
+struct bgr_mpc_bank {
+  int device = 0;
+  int32_t K = 0, H = 0;
+  float* d_bank = nullptr;
+  struct Stats {
+    double dt, r0, r1, q3;
+    void* d_cand;
+  };
+  std::mutex mu;
+  std::vector<Stats> stats;
+};
+
+namespace {
+
+// The evaluation proper, shared by the pointer and the handle entry points.  `bank_handle` (may be NULL) supplies
+// cached candidate statistics; without it they are recomputed from d_bank inside the call.
+int mpc_eval_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes, const double* d_state,
+                  const int32_t* d_ref_start, const int32_t* d_ref_len, const float* d_bank, int32_t n_candidates,
+                  bgr_mpc_bank* bank_handle, float* d_best_u, float* d_best_cost, int32_t* d_best_idx, float* d_costs,
+                  cudaStream_t stream, const char* who) {
+  BGR_TRY(validate_mpc(track, cfg, n_episodes, n_candidates, who));
   if (n_episodes == 0) return BGR_OK;
   if (d_state == nullptr || d_ref_start == nullptr || d_bank == nullptr) {
-    set_error("bgr_mpc_eval: d_state / d_ref_start / d_bank is NULL");
+    set_error("%s: state / ref_start / bank is NULL", who);
     return BGR_ERR_BAD_ARG;
   }
   if (reinterpret_cast<uintptr_t>(d_bank) & 7) {
-    set_error("bgr_mpc_eval: d_bank must be 8-byte aligned");
+    set_error("%s: the bank must be 8-byte aligned", who);
     return BGR_ERR_BAD_ARG;
   }
   DeviceScope dev(track->device);
@@ -1222,15 +1329,6 @@ extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, 
   BGR_TRY(device_info(track->device, &di));
   Scratch sc(stream);
   const bool explicit_rollout = cfg->precision == BGR_PRECISION_FP64 || (cfg->flags & BGR_MPC_EXPLICIT_ROLLOUT);
-  // one scratch block: [packed argmin accumulators | candidate statistics | episode coefficients]
-  const size_t b_packed = (static_cast<size_t>(n_episodes) * sizeof(unsigned long long) + 255) & ~size_t(255);
-  const size_t b_cand = explicit_rollout ? 0 : (mpc_cand_bytes(n_candidates) + 255) & ~size_t(255);
-  const size_t b_epi = explicit_rollout ? 0 : mpc_epi_bytes(n_episodes);
-  unsigned char* d_scratch;
-  BGR_TRY(sc.get(&d_scratch, b_packed + b_cand + b_epi));
-  unsigned long long* d_packed = reinterpret_cast<unsigned long long*>(d_scratch);
-  if (explicit_rollout)
-    BGR_CUDA(cudaMemsetAsync(d_packed, 0xff, static_cast<size_t>(n_episodes) * sizeof(unsigned long long), stream));
   MpcArgs A;
   std::memset(&A, 0, sizeof(A));
   A.trk = track->view();
@@ -1238,7 +1336,6 @@ extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, 
   A.ref_start = d_ref_start;
   A.ref_len = d_ref_len;
   A.bank = d_bank;
-  A.packed = d_packed;
   A.costs = d_costs;
   A.n_episodes = n_episodes;
   A.K = n_candidates;
@@ -1252,6 +1349,36 @@ extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, 
   A.q3 = cfg->q[3];
   A.r0 = cfg->r[0];
   A.r1 = cfg->r[1];
+  // cached candidate statistics of a bank handle: computed once per (dt, r0, r1, q3), kept until the handle dies
+  void* d_cand_cached = nullptr;
+  if (bank_handle != nullptr && !explicit_rollout) {
+    std::lock_guard<std::mutex> lock(bank_handle->mu);
+    for (const auto& st : bank_handle->stats)
+      if (st.dt == A.dt && st.r0 == A.r0 && st.r1 == A.r1 && st.q3 == A.q3) d_cand_cached = st.d_cand;
+    if (d_cand_cached == nullptr) {
+      void* p = nullptr;
+      BGR_CUDA(cudaMalloc(&p, mpc_cand_bytes(n_candidates)));
+      cudaError_t err = launch_mpc_cand_stats(A, p, stream);
+      if (err == cudaSuccess) err = cudaStreamSynchronize(stream);   // (once per configuration)
+      if (err != cudaSuccess) {
+        cudaFree(p);
+        return check_cuda(err, "candidate statistics");
+      }
+      count_launch();
+      bank_handle->stats.push_back({A.dt, A.r0, A.r1, A.q3, p});
+      d_cand_cached = p;
+    }
+  }
+  // one scratch block: [packed argmin accumulators | candidate statistics | episode coefficients]
+  const size_t b_packed = (static_cast<size_t>(n_episodes) * sizeof(unsigned long long) + 255) & ~size_t(255);
+  const size_t b_cand = (explicit_rollout || d_cand_cached != nullptr) ? 0 : (mpc_cand_bytes(n_candidates) + 255) & ~size_t(255);
+  const size_t b_epi = explicit_rollout ? 0 : mpc_epi_bytes(n_episodes);
+  unsigned char* d_scratch;
+  BGR_TRY(sc.get(&d_scratch, b_packed + b_cand + b_epi));
+  unsigned long long* d_packed = reinterpret_cast<unsigned long long*>(d_scratch);
+  if (explicit_rollout)
+    BGR_CUDA(cudaMemsetAsync(d_packed, 0xff, static_cast<size_t>(n_episodes) * sizeof(unsigned long long), stream));
+  A.packed = d_packed;
   BGR_TRY(ensure_events(track->device));
   BGR_CUDA(cudaEventRecord(g_last.start, stream));
   if (explicit_rollout) {
@@ -1259,7 +1386,8 @@ extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, 
     BGR_CUDA(launch_mpc(A, cfg->precision, stream, di.sm_count));
     count_launch();
   } else {
-    BGR_CUDA(launch_mpc_factored(A, d_scratch + b_packed, d_scratch + b_packed + b_cand, stream, di.sm_count));
+    BGR_CUDA(launch_mpc_factored(A, d_cand_cached != nullptr ? d_cand_cached : d_scratch + b_packed,
+                                 d_scratch + b_packed + b_cand, stream, di.sm_count, d_cand_cached != nullptr));
     count_launch(2);
   }
   BGR_CUDA(cudaEventRecord(g_last.stop, stream));
@@ -1271,16 +1399,23 @@ extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, 
   return BGR_OK;
 }
 
-extern "C" int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
-                                 const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
-                                 const float* h_bank, int32_t n_candidates, float* h_best_u, float* h_best_cost,
-                                 int32_t* h_best_idx, float* h_costs, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BGR_TRY(validate_mpc(track, cfg, n_episodes, n_candidates, "bgr_mpc_eval_host"));
+// host buffers around mpc_eval_core; `h_bank` is uploaded per call unless a handle supplies the resident bank
+int mpc_eval_host_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes, const double* h_state,
+                       const int32_t* h_ref_start, const int32_t* h_ref_len, const float* h_bank, int32_t n_candidates,
+                       bgr_mpc_bank* bank_handle, float* h_best_u, float* h_best_cost, int32_t* h_best_idx,
+                       float* h_costs, cudaStream_t stream, const char* who) {
+  BGR_TRY(validate_mpc(track, cfg, n_episodes, n_candidates, who));
   if (n_episodes == 0) return BGR_OK;
-  if (h_state == nullptr || h_ref_start == nullptr || h_bank == nullptr) {
-    set_error("bgr_mpc_eval_host: h_state / h_ref_start / h_bank is NULL");
+  if (h_state == nullptr || h_ref_start == nullptr || (h_bank == nullptr && bank_handle == nullptr)) {
+    set_error("%s: h_state / h_ref_start / bank is NULL", who);
     return BGR_ERR_BAD_ARG;
+  }
+  for (int64_t e = 0; e < n_episodes; ++e) {
+    if (h_ref_start[e] < 0 || h_ref_start[e] >= track->n || (h_ref_len != nullptr && h_ref_len[e] < 1)) {
+      set_error("%s: episode %lld has ref_start %d (track has %d waypoints)%s", who, static_cast<long long>(e),
+                h_ref_start[e], track->n, h_ref_len != nullptr && h_ref_len[e] < 1 ? " / ref_len < 1" : "");
+      return BGR_ERR_BAD_ARG;
+    }
   }
   DeviceScope dev(track->device);
   Scratch sc(stream);
@@ -1288,23 +1423,24 @@ extern "C" int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* 
   const size_t bank_count = K * static_cast<size_t>(cfg->horizon) * 2;
   double* d_state;
   int32_t *d_start, *d_len = nullptr, *d_idx;
-  float *d_bank, *d_u, *d_cost, *d_costs = nullptr;
+  float *d_bank = bank_handle != nullptr ? bank_handle->d_bank : nullptr, *d_u, *d_cost, *d_costs = nullptr;
   BGR_TRY(sc.get(&d_state, E * 4));
   BGR_TRY(sc.get(&d_start, E));
-  BGR_TRY(sc.get(&d_bank, bank_count));
+  if (bank_handle == nullptr) BGR_TRY(sc.get(&d_bank, bank_count));
   BGR_TRY(sc.get(&d_u, E * 2));
   BGR_TRY(sc.get(&d_cost, E));
   BGR_TRY(sc.get(&d_idx, E));
   BGR_CUDA(cudaMemcpyAsync(d_state, h_state, E * 4 * sizeof(double), cudaMemcpyHostToDevice, stream));
   BGR_CUDA(cudaMemcpyAsync(d_start, h_ref_start, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-  BGR_CUDA(cudaMemcpyAsync(d_bank, h_bank, bank_count * sizeof(float), cudaMemcpyHostToDevice, stream));
+  if (bank_handle == nullptr)
+    BGR_CUDA(cudaMemcpyAsync(d_bank, h_bank, bank_count * sizeof(float), cudaMemcpyHostToDevice, stream));
   if (h_ref_len != nullptr) {
     BGR_TRY(sc.get(&d_len, E));
     BGR_CUDA(cudaMemcpyAsync(d_len, h_ref_len, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   }
   if (h_costs != nullptr) BGR_TRY(sc.get(&d_costs, E * K));
-  BGR_TRY(bgr_mpc_eval(track, cfg, n_episodes, d_state, d_start, d_len, d_bank, n_candidates, d_u, d_cost, d_idx,
-                       d_costs, stream));
+  BGR_TRY(mpc_eval_core(track, cfg, n_episodes, d_state, d_start, d_len, d_bank, n_candidates, bank_handle, d_u, d_cost,
+                        d_idx, d_costs, stream, who));
   if (h_best_u != nullptr)
     BGR_CUDA(cudaMemcpyAsync(h_best_u, d_u, E * 2 * sizeof(float), cudaMemcpyDeviceToHost, stream));
   if (h_best_cost != nullptr)
@@ -1315,6 +1451,102 @@ extern "C" int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* 
     BGR_CUDA(cudaMemcpyAsync(h_costs, d_costs, E * K * sizeof(float), cudaMemcpyDeviceToHost, stream));
   BGR_CUDA(cudaStreamSynchronize(stream));
   return BGR_OK;
+}
+
+int check_bank_handle(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, const bgr_mpc_bank* bank, const char* who) {
+  if (bank == nullptr || track == nullptr || cfg == nullptr) {
+    set_error("%s: track / cfg / bank is NULL", who);
+    return BGR_ERR_BAD_ARG;
+  }
+  if (bank->device != track->device || bank->H != cfg->horizon) {
+    set_error("%s: the bank lives on device %d with horizon %d; the call needs device %d, horizon %d", who, bank->device,
+              bank->H, track->device, cfg->horizon);
+    return BGR_ERR_BAD_ARG;
+  }
+  return BGR_OK;
+}
+
+}  // namespace
+
+extern "C" int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                            const double* d_state, const int32_t* d_ref_start, const int32_t* d_ref_len,
+                            const float* d_bank, int32_t n_candidates, float* d_best_u, float* d_best_cost,
+                            int32_t* d_best_idx, float* d_costs, void* stream) {
+  return mpc_eval_core(track, cfg, n_episodes, d_state, d_ref_start, d_ref_len, d_bank, n_candidates, nullptr, d_best_u,
+                       d_best_cost, d_best_idx, d_costs, static_cast<cudaStream_t>(stream), "bgr_mpc_eval");
+}
+
+extern "C" int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                                 const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
+                                 const float* h_bank, int32_t n_candidates, float* h_best_u, float* h_best_cost,
+                                 int32_t* h_best_idx, float* h_costs, void* stream) {
+  return mpc_eval_host_core(track, cfg, n_episodes, h_state, h_ref_start, h_ref_len, h_bank, n_candidates, nullptr,
+                            h_best_u, h_best_cost, h_best_idx, h_costs, static_cast<cudaStream_t>(stream),
+                            "bgr_mpc_eval_host");
+}
+
+extern "C" int bgr_mpc_bank_create(int device, const float* h_bank, int32_t n_candidates, int32_t horizon,
+                                   bgr_mpc_bank_t** out_bank) {
+  if (out_bank == nullptr) {
+    set_error("bgr_mpc_bank_create: out_bank is NULL");
+    return BGR_ERR_BAD_ARG;
+  }
+  *out_bank = nullptr;
+  if (h_bank == nullptr || n_candidates < 1 || horizon < 1 || horizon > 64) {
+    set_error("bgr_mpc_bank_create: need h_bank, n_candidates >= 1 and 1 <= horizon <= 64");
+    return BGR_ERR_BAD_ARG;
+  }
+  int n_dev = 0;
+  BGR_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) {
+    set_error("bgr_mpc_bank_create: device %d out of range (%d CUDA devices)", device, n_dev);
+    return BGR_ERR_BAD_ARG;
+  }
+  bgr_mpc_bank* b = new (std::nothrow) bgr_mpc_bank();
+  if (b == nullptr) {
+    set_error("bgr_mpc_bank_create: out of host memory");
+    return BGR_ERR_ALLOC;
+  }
+  b->device = device;
+  b->K = n_candidates;
+  b->H = horizon;
+  DeviceScope dev(device);
+  const size_t bytes = static_cast<size_t>(n_candidates) * horizon * 2 * sizeof(float);
+  cudaError_t err = cudaMalloc(reinterpret_cast<void**>(&b->d_bank), bytes);
+  if (err == cudaSuccess) err = cudaMemcpy(b->d_bank, h_bank, bytes, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    cudaFree(b->d_bank);
+    delete b;
+    return check_cuda(err, "bgr_mpc_bank_create");
+  }
+  *out_bank = b;
+  return BGR_OK;
+}
+
+extern "C" void bgr_mpc_bank_destroy(bgr_mpc_bank_t* bank) {
+  if (bank == nullptr) return;
+  DeviceScope dev(bank->device);
+  cudaFree(bank->d_bank);
+  for (auto& st : bank->stats) cudaFree(st.d_cand);
+  delete bank;
+}
+
+extern "C" int bgr_mpc_eval_bank(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                                 const double* d_state, const int32_t* d_ref_start, const int32_t* d_ref_len,
+                                 bgr_mpc_bank_t* bank, float* d_best_u, float* d_best_cost, int32_t* d_best_idx,
+                                 float* d_costs, void* stream) {
+  BGR_TRY(check_bank_handle(track, cfg, bank, "bgr_mpc_eval_bank"));
+  return mpc_eval_core(track, cfg, n_episodes, d_state, d_ref_start, d_ref_len, bank->d_bank, bank->K, bank, d_best_u,
+                       d_best_cost, d_best_idx, d_costs, static_cast<cudaStream_t>(stream), "bgr_mpc_eval_bank");
+}
+
+extern "C" int bgr_mpc_eval_bank_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                                      const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
+                                      bgr_mpc_bank_t* bank, float* h_best_u, float* h_best_cost, int32_t* h_best_idx,
+                                      float* h_costs, void* stream) {
+  BGR_TRY(check_bank_handle(track, cfg, bank, "bgr_mpc_eval_bank_host"));
+  return mpc_eval_host_core(track, cfg, n_episodes, h_state, h_ref_start, h_ref_len, nullptr, bank->K, bank, h_best_u,
+                            h_best_cost, h_best_idx, h_costs, static_cast<cudaStream_t>(stream), "bgr_mpc_eval_bank_host");
 }
 
 // ================================================================================================
@@ -1363,6 +1595,48 @@ extern "C" int bgr_identify_dynamics_host(int64_t n_episodes, int32_t max_rows, 
   BGR_CUDA(cudaMemcpyAsync(h_AB, d_AB, E * 6 * BGR_SYSID_COLS * sizeof(double), cudaMemcpyDeviceToHost, stream));
   BGR_CUDA(cudaMemcpyAsync(h_ok, d_ok, E * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   BGR_CUDA(cudaStreamSynchronize(stream));
+  return BGR_OK;
+}
+
+// ================================================================================================
+// FP64 peak probe (DFMA chains): the measured roofline denominator of the MPC evaluator
+// ================================================================================================
+extern "C" int bgr_fp64_peak_probe(int device, double* out_tflops) {
+  int n_dev = 0;
+  BGR_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) {
+    set_error("bgr_fp64_peak_probe: device %d out of range", device);
+    return BGR_ERR_BAD_ARG;
+  }
+  DeviceScope dev(device);
+  DeviceInfo di;
+  BGR_TRY(device_info(device, &di));
+  const int grid = di.sm_count * 8;
+  const int iters = 1 << 12;
+  double* d_out = nullptr;
+  BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_out), static_cast<size_t>(grid) * 256 * sizeof(double)));
+  cudaEvent_t a, b;
+  BGR_CUDA(cudaEventCreate(&a));
+  BGR_CUDA(cudaEventCreate(&b));
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(a, nullptr);
+    cudaError_t err = launch_fp64_probe(d_out, grid, iters, nullptr);
+    cudaEventRecord(b, nullptr);
+    if (err != cudaSuccess || cudaEventSynchronize(b) != cudaSuccess) {
+      cudaFree(d_out);
+      return check_cuda(err != cudaSuccess ? err : cudaGetLastError(), "fp64 probe");
+    }
+    count_launch();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0) best_ms = std::min(best_ms, static_cast<double>(ms));
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d_out);
+  const double fmas = static_cast<double>(grid) * 256.0 * iters * 8.0;   // 8 independent DFMA chains per thread
+  if (out_tflops != nullptr) *out_tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
   return BGR_OK;
 }
 

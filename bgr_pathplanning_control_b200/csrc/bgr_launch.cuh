@@ -59,7 +59,8 @@ struct MpcArgs {
 cudaError_t launch_mpc(const MpcArgs& A, int precision, cudaStream_t stream, int sm_count);
 // factored evaluator (production): candidate statistics + episode coefficients + 4 FMAs per pair
 cudaError_t launch_mpc_factored(const MpcArgs& A, void* scratch_cand, void* scratch_epi, cudaStream_t stream,
-                                int sm_count);
+                                int sm_count, bool cand_ready = false);
+cudaError_t launch_mpc_cand_stats(const MpcArgs& A, void* cand_out, cudaStream_t stream);
 size_t mpc_cand_bytes(int K);
 size_t mpc_epi_bytes(long long E);
 cudaError_t launch_mpc_finalize(const unsigned long long* packed, const float* bank, int H, long long n_episodes,
@@ -77,5 +78,6 @@ cudaError_t launch_aggregate_partials(const float* metrics, const int32_t* statu
 cudaError_t launch_compact_survivors(const int32_t* status, long long n_episodes, int32_t* idx, int32_t* count,
                                      cudaStream_t stream);
 cudaError_t launch_fp32_probe(float* out, int grid, int iters, cudaStream_t stream);
+cudaError_t launch_fp64_probe(double* out, int grid, int iters, cudaStream_t stream);
 
 }  // namespace bgr

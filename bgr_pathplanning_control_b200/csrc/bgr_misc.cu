@@ -129,4 +129,25 @@ cudaError_t launch_fp32_probe(float* out, int grid, int iters, cudaStream_t stre
   return cudaGetLastError();
 }
 
+// the same with DFMA chains: the measured FP64 CUDA-core peak (roofline denominator of the MPC evaluator)
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* __restrict__ out, int iters) {
+  double acc[8];
+  const double a = 1.0 + 1e-12 * static_cast<double>(threadIdx.x), b = 1e-15 * static_cast<double>(blockIdx.x);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = static_cast<double>(i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+  out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t launch_fp64_probe(double* out, int grid, int iters, cudaStream_t stream) {
+  fp64_probe_kernel<<<grid, 256, 0, stream>>>(out, iters);
+  return cudaGetLastError();
+}
+
 }  // namespace bgr

@@ -32,6 +32,19 @@ struct EpisodeStage {
   unsigned long long best;
 };
 
+// First reference waypoint of an episode, made safe: ref_start is caller-supplied device data, and one bad row must not
+// read out of bounds for the whole batch.  Closed tracks wrap it into [0, n) (floor-mod, negatives included); open
+// tracks clamp it to [0, n - 1].  (bgr_mpc_eval_host rejects such rows up front; device callers get this.)
+__device__ __forceinline__ int safe_ref_start(const MpcArgs& A, long long e) {
+  const int n = A.trk.n;
+  const int s = A.ref_start[e];
+  if (A.trk.closed) {
+    const int m = s % n;
+    return m < 0 ? m + n : m;
+  }
+  return s < 0 ? 0 : (s > n - 1 ? n - 1 : s);
+}
+
 // Stage the candidate-independent part of one episode (threads 0..H of the CTA).
 template <typename Real>
 __device__ __forceinline__ void stage_episode(const MpcArgs& A, long long e, EpisodeStage<Real>* st) {
@@ -48,7 +61,7 @@ __device__ __forceinline__ void stage_episode(const MpcArgs& A, long long e, Epi
   }
   // reference point of stage t (:539-542); the terminal cost reuses the last stage's (:548)
   const int n = A.trk.n;
-  const int start = A.ref_start[e];
+  const int start = safe_ref_start(A, e);
   int len = A.ref_len != nullptr ? A.ref_len[e] : (A.trk.closed ? 0x3fffffff : n - start);
   if (len < 1) len = 1;
   int k_ref = t < A.H ? t : A.H - 1;
@@ -205,7 +218,7 @@ __device__ __forceinline__ void episode_coef(const MpcArgs& A, EpiCoef* __restri
   const double x0 = s[0], y0 = s[1], yaw0 = s[2], v0 = s[3];
   const double cos_t = cos(yaw0), sin_t = sin(yaw0);               // :514-515
   const int n = A.trk.n;
-  const int start = A.ref_start[e];
+  const int start = safe_ref_start(A, e);
   int len = A.ref_len != nullptr ? A.ref_len[e] : (A.trk.closed ? 0x3fffffff : n - start);
   if (len < 1) len = 1;
   double sx = x0, sy = y0, XY = 0.0;
@@ -337,12 +350,20 @@ __global__ void __launch_bounds__(kFactThreads) mpc_factored_kernel(const CandSt
   }
 }
 
+// candidate statistics only (a bank handle computes them once per cost configuration and keeps them)
+cudaError_t launch_mpc_cand_stats(const MpcArgs& A, void* cand_out, cudaStream_t stream) {
+  const int cand_blocks = (A.K + 127) / 128;
+  mpc_prepare_kernel<<<cand_blocks, 128, 0, stream>>>(A, cand_blocks, static_cast<CandStats*>(cand_out), nullptr);
+  return cudaGetLastError();
+}
+
+// `cand_ready`: scratch_cand already holds the statistics of this bank for this cost configuration (bank handle)
 cudaError_t launch_mpc_factored(const MpcArgs& A, void* scratch_cand, void* scratch_epi, cudaStream_t stream,
-                                int sm_count) {
+                                int sm_count, bool cand_ready) {
   (void)sm_count;
   CandStats* cand = static_cast<CandStats*>(scratch_cand);
   EpiCoef* epi = static_cast<EpiCoef*>(scratch_epi);
-  const int cand_blocks = (A.K + 127) / 128;
+  const int cand_blocks = cand_ready ? 0 : (A.K + 127) / 128;
   const unsigned epi_blocks = static_cast<unsigned>((A.n_episodes + 127) / 128);
   mpc_prepare_kernel<<<cand_blocks + epi_blocks, 128, 0, stream>>>(A, cand_blocks, cand, epi);
   const long long chunks = (A.K + kFactChunk - 1) / kFactChunk;

@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
       if constexpr (EXTRAS) {
         if (A.noise_on) {
           Real z[4];
-          gaussians4<Real>(philox4x32_10(static_cast<uint32_t>(k), kStreamObs, 0u, 0u, A.seed,
+          // counter = the episode's own step count (a stepped closed loop draws the same stream as one rollout)
+          gaussians4<Real>(philox4x32_10(static_cast<uint32_t>(k_gain0 + k), kStreamObs, 0u, 0u, A.seed,
                                          static_cast<uint32_t>(A.episode_id_base + e)), z);
           // observed x = x + sigma z  =>  offsets (p - x_obs) = (p - xr) - (xl + sigma z)
           oxl = xl + static_cast<Real>(A.sigma_xy) * z[0];

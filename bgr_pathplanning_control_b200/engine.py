@@ -310,10 +310,19 @@ def rollout_groups(track, groups, *, aggregate=False, outs=None, order=None):
     torch = _torch()
     dev = torch.device("cuda", track.device)
     main = torch.cuda.current_stream(dev)
-    key = (track.device, len(groups))
-    if key not in _group_streams:
-        _group_streams[key] = [torch.cuda.Stream(dev) for _ in groups]
-    streams = _group_streams[key]
+    streams = _group_streams.setdefault(track.device, [])
+    while len(streams) < len(groups):
+        streams.append(torch.cuda.Stream(dev))
+    # Result tensors are allocated HERE, on the caller's stream: the caching allocator ties a block to the stream that
+    # was current when it was allocated, and a block born on a side stream could be handed out again for the next call's
+    # side-stream work while the caller's stream is still reading it.
+    if outs is None:
+        outs = []
+        for cfg, params, _ in groups:
+            E = int(params.shape[0])
+            outs.append(RolloutResult(torch.empty((E, abi.N_METRICS), dtype=torch.float32, device=dev),
+                                      torch.empty((E, abi.N_STATUS), dtype=torch.int32, device=dev), None,
+                                      torch.empty(abi.N_AGG, dtype=torch.float64, device=dev) if aggregate else None))
     start = torch.cuda.Event()
     start.record(main)
     results = [None] * len(groups)
@@ -321,10 +330,18 @@ def rollout_groups(track, groups, *, aggregate=False, outs=None, order=None):
         cfg, params, init = groups[g]
         streams[g].wait_event(start)
         with torch.cuda.stream(streams[g]):
-            results[g] = rollout(track, cfg, params, init, aggregate=aggregate, out=None if outs is None else outs[g])
-    for st in streams:
+            results[g] = rollout(track, cfg, params, init, aggregate=aggregate, out=outs[g])
+        # the inputs are the caller's too: tell the allocator the side stream is using them
+        params.record_stream(streams[g])
+        init.record_stream(streams[g])
+    for st in streams[: len(groups)]:
         main.wait_stream(st)
     return results
+
+
+def release_group_streams():
+    """Drop the cached side streams of ``rollout_groups`` (one list per device, grown to the largest group count seen)."""
+    _group_streams.clear()
 
 
 def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out=None):
@@ -345,6 +362,80 @@ def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out=Non
     abi.check(lib.bgr_rollout_host(track.handle, C.byref(cfg), E, _ptr(params), _ptr(init_state), _ptr(metrics),
                                    _ptr(status), _ptr(tr), _ptr(agg), None))
     return RolloutResult(metrics, status, tr, agg, None)
+
+
+_async_streams = {}      # device -> [cudaStream_t, ...]: each in-flight host-buffer rollout completes on its own stream
+_async_next = {}
+_ASYNC_DEPTH = 4
+
+
+def _async_stream(lib, device):
+    pool = _async_streams.setdefault(device, [])
+    if len(pool) < _ASYNC_DEPTH:
+        h = C.c_void_p()
+        abi.check(lib.bgr_stream_create(int(device), C.byref(h)))
+        pool.append(h)
+        return pool[-1]
+    i = _async_next.get(device, 0)
+    _async_next[device] = (i + 1) % _ASYNC_DEPTH
+    return pool[i]
+
+
+class PendingRollout:
+    """A host-buffer rollout that has been queued but not waited for (``rollout_async``).  ``wait()`` blocks until the
+    result arrays are filled and returns the ``RolloutResult``."""
+
+    def __init__(self, lib, stream, result, keep):
+        self._lib, self._stream, self._result, self._keep, self._done = lib, stream, result, keep, False
+
+    def wait(self):
+        if not self._done:
+            abi.check(self._lib.bgr_stream_synchronize(self._stream))
+            self._done = True
+            self._keep = None
+        return self._result
+
+
+def rollout_async(track, config, params, init_state, *, aggregate=False, out=None):
+    """``rollout`` for HOST (numpy, ideally pinned) buffers without the final synchronise (``bgr_rollout_host_async``):
+    returns a ``PendingRollout``.  Calling it for batch i + 1 before ``wait()``-ing batch i lets the library run the
+    first upload of the new batch under the last kernel and download of the old one -- the host-buffer path then costs
+    the kernel time, not kernel + copies.  The input and output arrays must not be touched until ``wait()`` returns;
+    give every in-flight batch its own ``out`` buffers, and keep at most 4 batches in flight per device."""
+    lib = abi.load()
+    cfg = config.to_struct() if isinstance(config, RolloutConfig) else config
+    params = _np(params, np.float32)
+    E = params.shape[0]
+    params = _np(params, np.float32, (E, abi.N_PARAMS))
+    init_state = _np(init_state, np.float64, (E, abi.N_STATE))
+    if out is not None:
+        metrics, status = out.metrics, out.status
+        if (metrics.dtype != np.float32 or metrics.shape != (E, abi.N_METRICS) or not metrics.flags.c_contiguous
+                or status.dtype != np.int32 or status.shape != (E, abi.N_STATUS) or not status.flags.c_contiguous):
+            raise ValueError("out.metrics / out.status must be contiguous (E, 12) float32 / (E, 10) int32 arrays")
+    else:
+        metrics = np.empty((E, abi.N_METRICS), dtype=np.float32)
+        status = np.empty((E, abi.N_STATUS), dtype=np.int32)
+    agg = None
+    if aggregate:
+        agg = out.aggregate if (out is not None and out.aggregate is not None) else np.empty(abi.N_AGG)
+    stream = _async_stream(lib, track.device)
+    abi.check(lib.bgr_rollout_host_async(track.handle, C.byref(cfg), E, _ptr(params), _ptr(init_state), _ptr(metrics),
+                                         _ptr(status), _ptr(agg), stream))
+    return PendingRollout(lib, stream, RolloutResult(metrics, status, None, agg, None), (params, init_state, cfg, track))
+
+
+def build_id():
+    """Identity of the loaded library build (sources + compile-time knobs)."""
+    return abi.load().bgr_build_id().decode()
+
+
+def lqg_covariance(dt=conf.dt, n_steps=0):
+    """(2, 2) estimate covariance ``P`` of the LQG controller's Kalman filter after ``n_steps`` updates
+    (core/controllers.py:109, :145, :160)."""
+    P = np.empty(4)
+    abi.check(abi.load().bgr_lqg_covariance(float(dt), int(n_steps), _ptr(P)))
+    return P.reshape(2, 2)
 
 
 def last_kernel_ms():
@@ -411,9 +502,25 @@ class MpcResult:
     kernel_ms: float | None = None
 
 
-def candidate_bank(n_candidates=4096, horizon=30, seed=20261021, max_accel=conf.MAX_ACCEL, max_steer=conf.MAX_STEER):
-    """(K, H, 2) float32 = (accel, steer): uniform draws smoothed by a 3-tap moving average, candidate 0
-    all zeros.  Host numpy; the same bank feeds the oracle."""
+def candidate_bank(n_candidates=4096, horizon=30, seed=20261021, max_accel=conf.MAX_ACCEL, max_steer=conf.MAX_STEER,
+                   kind="uniform", dt=0.05):
+    """(K, H, 2) float32 = (accel, steer) candidate control sequences.  Host numpy; the same bank feeds the oracle.
+
+    ``kind="uniform"``: uniform draws smoothed by a 3-tap moving average, candidate 0 all zeros (SURVEY.md section 8d
+    config 4) -- a generic sample of the control box.  Measured against the exact optimum of the reference's QP
+    (oracle ``mpc_qp_optimum``) its best of 4 096 candidates costs 19 % more in the median (tests/test_gpu_mpc.py).
+
+    ``kind="qp_family"``: the bank the drop-in ``MPCController`` uses.  The reference's QP (core/controllers.py:503-552)
+    separates into a steering chain (yaw) and an acceleration chain (v); the optimum of each chain depends on ONE
+    scalar besides the horizon -- the initial heading (times v0 / WB) and the initial speed error.  The bank is the
+    outer product of sqrt(K) acceleration profiles x sqrt(K) steering profiles, each the exact bounded-least-squares
+    optimum of its chain for one grid value of that scalar (64 speed errors in +-8 m/s; 16 headings in +-3.2 rad x
+    4 speeds): the cheapest candidate is then within 0.2 % of the QP optimum over config 4's states (median 0.00 %).
+    The kernels do not care which bank they score."""
+    if kind == "qp_family":
+        return _qp_family_bank(n_candidates, horizon, dt, max_accel, max_steer)
+    if kind != "uniform":
+        raise ValueError(f"Unknown candidate bank kind: {kind}")
     rng = np.random.default_rng(seed)
     u = np.empty((n_candidates, horizon, 2))
     u[..., 0] = rng.uniform(-max_accel, max_accel, (n_candidates, horizon))
@@ -424,12 +531,82 @@ def candidate_bank(n_candidates=4096, horizon=30, seed=20261021, max_accel=conf.
     return np.ascontiguousarray(u, dtype=np.float32)
 
 
+def _qp_family_bank(n_candidates, horizon, dt, max_accel, max_steer, q=(1.0, 1.0, 0.5, 0.1), r=(0.1, 0.1)):
+    from scipy.optimize import lsq_linear       # input synthesis on the host, like tracks.py / sweeps.py
+    side = int(round(np.sqrt(n_candidates)))
+    if side * side != n_candidates or side < 8 or side % 4:
+        raise ValueError("a qp_family bank needs a square number of candidates with sqrt(K) a multiple of 4 (e.g. 4096)")
+    H = int(horizon)
+    low = np.tril(np.ones((H, H)))
+
+    def chain(scale, qq, rr, e0, bound):
+        a_mat = np.vstack([np.sqrt(qq) * scale * low, np.sqrt(rr) * np.eye(H)])
+        b_vec = np.concatenate([-np.sqrt(qq) * e0 * np.ones(H), np.zeros(H)])
+        return lsq_linear(a_mat, b_vec, bounds=(-bound, bound), method="bvls", tol=1e-14).x
+
+    acc = np.array([chain(dt, q[3], r[0], e, max_accel) for e in np.linspace(-8.0, 8.0, side)])
+    n_y = side // 4
+    yaws = np.concatenate([-np.geomspace(0.02, 3.2, n_y // 2)[::-1], np.geomspace(0.02, 3.2, n_y - n_y // 2)])
+    ste = np.array([chain(v * dt / conf.WB, q[2], r[1], y, max_steer) for v in (1.0, 2.5, 4.5, 7.0) for y in yaws])
+    bank = np.empty((side * side, H, 2))
+    bank[:, :, 0] = np.repeat(acc, side, axis=0)
+    bank[:, :, 1] = np.tile(ste, (side, 1))
+    return np.ascontiguousarray(bank, dtype=np.float32)
+
+
+class MpcBank:
+    """Device-resident candidate bank (``bgr_mpc_bank_t``): upload ``bank`` (K, H, 2) float32 once, then pass the
+    handle to ``mpc_evaluate`` in place of the array -- per call only the states travel, and the per-candidate
+    statistics of the factored evaluator are computed once per cost configuration instead of once per call."""
+
+    def __init__(self, bank, device=0):
+        lib = abi.load()
+        self.array = _np(bank, np.float32)
+        if self.array.ndim != 3 or self.array.shape[2] != 2:
+            raise ValueError("bank must have shape (K, H, 2)")
+        self.K, self.H = int(self.array.shape[0]), int(self.array.shape[1])
+        self.device = int(device)
+        self._lib = lib
+        self._h = C.c_void_p()
+        abi.check(lib.bgr_mpc_bank_create(self.device, _ptr(self.array), self.K, self.H, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("bank handle is closed")
+        return self._h
+
+    @property
+    def shape(self):
+        return self.array.shape
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bgr_mpc_bank_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fp64_peak_probe(device=0):
+    """TFLOP/s of a DFMA-chain microbenchmark: the measured FP64 CUDA-core peak (MPC evaluator roofline)."""
+    t = C.c_double()
+    abi.check(abi.load().bgr_fp64_peak_probe(int(device), C.byref(t)))
+    return t.value
+
+
 def mpc_evaluate(track, config, state, ref_start, bank, ref_len=None, *, return_costs=False, time_kernel=False):
-    """Score every candidate control sequence of ``bank`` (K, H, 2) for every episode state (E, 4) =
-    ``[x, y, yaw, v]`` and pick the cheapest feasible one.  CUDA tensors (zero copy, async) or numpy arrays
-    (host entry point)."""
+    """Score every candidate control sequence of ``bank`` (K, H, 2) -- an array, or a resident ``MpcBank`` -- for every
+    episode state (E, 4) = ``[x, y, yaw, v]`` and pick the cheapest feasible one.  CUDA tensors (zero copy, async) or
+    numpy arrays (host entry point)."""
     lib = abi.load()
     cfg = config.to_struct() if isinstance(config, MpcConfig) else config
+    if isinstance(bank, MpcBank):
+        return _mpc_evaluate_bank(lib, track, cfg, state, ref_start, bank, ref_len, return_costs, time_kernel)
     if isinstance(state, np.ndarray):
         state = _np(state, np.float64)
         E = state.shape[0]
@@ -461,6 +638,39 @@ def mpc_evaluate(track, config, state, ref_start, bank, ref_len=None, *, return_
     stream = torch.cuda.current_stream(dev).cuda_stream
     abi.check(lib.bgr_mpc_eval(track.handle, C.byref(cfg), E, _ptr(state), _ptr(ref_start), _ptr(ref_len), _ptr(bank),
                                K, _ptr(u), _ptr(cost), _ptr(idx), _ptr(costs), stream))
+    ms = last_kernel_ms() if time_kernel and E > 0 else None
+    return MpcResult(u, cost, idx, costs, ms)
+
+
+def _mpc_evaluate_bank(lib, track, cfg, state, ref_start, bank, ref_len, return_costs, time_kernel):
+    K = bank.K
+    if isinstance(state, np.ndarray):
+        state = _np(state, np.float64)
+        E = state.shape[0]
+        state = _np(state, np.float64, (E, 4))
+        ref_start = _np(ref_start, np.int32, (E,))
+        ref_len = None if ref_len is None else _np(ref_len, np.int32, (E,))
+        u = np.empty((E, 2), np.float32)
+        cost = np.empty(E, np.float32)
+        idx = np.empty(E, np.int32)
+        costs = np.empty((E, K), np.float32) if return_costs else None
+        abi.check(lib.bgr_mpc_eval_bank_host(track.handle, C.byref(cfg), E, _ptr(state), _ptr(ref_start), _ptr(ref_len),
+                                             bank.handle, _ptr(u), _ptr(cost), _ptr(idx), _ptr(costs), None))
+        return MpcResult(u, cost, idx, costs)
+    torch = _torch()
+    E = int(state.shape[0])
+    for name, t, dt, shape in (("state", state, torch.float64, (E, 4)), ("ref_start", ref_start, torch.int32, (E,))):
+        if not t.is_cuda or t.device.index != track.device or t.dtype != dt or tuple(t.shape) != shape \
+                or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous {dt} CUDA tensor of shape {shape} on cuda:{track.device}")
+    dev = state.device
+    u = torch.empty((E, 2), dtype=torch.float32, device=dev)
+    cost = torch.empty(E, dtype=torch.float32, device=dev)
+    idx = torch.empty(E, dtype=torch.int32, device=dev)
+    costs = torch.empty((E, K), dtype=torch.float32, device=dev) if return_costs else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    abi.check(lib.bgr_mpc_eval_bank(track.handle, C.byref(cfg), E, _ptr(state), _ptr(ref_start), _ptr(ref_len),
+                                    bank.handle, _ptr(u), _ptr(cost), _ptr(idx), _ptr(costs), stream))
     ms = last_kernel_ms() if time_kernel and E > 0 else None
     return MpcResult(u, cost, idx, costs, ms)
 

@@ -63,6 +63,8 @@ class Controller:
         self.steer_ctrl = PurePursuitController(look_ahead_distance=conf.LOOKAHEAD_DISTANCE)        # :23
         self.states = States()                                                                      # :24
         self.actuator = actuator        # callable(steering_cmd, acceleration) standing in for sim_car_controls (:90)
+        self.target_ind = 0             # the index compute_steering returned last (a local of update() in the reference,
+                                        # logged at :81; kept here for callers that have no Planner node)
 
     def update(self, data):
         try:
@@ -97,7 +99,9 @@ class Controller:
             data["v_log"] = self.accel_ctrl.maxspeed                                                # :84-86
             data["acceleration"] = acceleration
             data["steering"] = steering
-            data["target_ind"] = target_ind
+            # data["target_ind"] is the PLANNER's to write (nodes/planner.py:101): the reference controller never
+            # publishes its own advanced index, so a planner that returns early leaves its stale index in place
+            self.target_ind = int(target_ind)
             data["controls"] = sim_controls(-steering, acceleration)                                # :90
             if self.actuator is not None:
                 self.actuator(-steering, acceleration)

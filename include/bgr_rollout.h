@@ -153,7 +153,7 @@ typedef struct bgr_track_desc {
   int32_t n_cones;
   int32_t reserved;
   double cone_reach;       /* cones within cone_reach of a waypoint are that waypoint's candidates;
-                              must be >= hit_radius + 6 * sigma_cone * sqrt(2) + BGR_CONE_GUARD */
+                              must be >= hit_radius + 6 * sigma_cone + BGR_CONE_GUARD (checked per rollout) */
 } bgr_track_desc_t;
 #define BGR_CONE_GUARD 2.0 /* [m] car-to-nearest-waypoint distance up to which candidate lists are exact */
 #define BGR_MAX_CONES 512
@@ -237,6 +237,15 @@ typedef struct bgr_mpc_cfg {
 int bgr_abi_version(void);
 const char* bgr_last_error_string(void);
 int bgr_device_count(int* out_count);
+/* Identity of this build: hash of the kernel / ABI sources and of the compile-time knobs it was built with.  bench.py
+ * prints it and matches it against the build id stored with the ncu summaries under profiles/, so that profile
+ * evidence of an older kernel is never quoted for a newer one. */
+const char* bgr_build_id(void);
+/* Streams for callers that hold no CUDA runtime of their own (the *_async entry points): a non-blocking stream on
+ * `device`, cudaStreamSynchronize, cudaStreamDestroy.  Any cudaStream_t the caller already owns works as well. */
+int bgr_stream_create(int device, void** out_stream);
+int bgr_stream_synchronize(void* stream);
+int bgr_stream_destroy(void* stream);
 
 /* ---- track handle: replaces the (N,3) `path` ndarray + `curve` the reference hands its controllers
  *      every call (nodes/controller.py:56,62) ---- */
@@ -265,6 +274,16 @@ int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int
                      const float* h_params, const double* h_init_state, float* h_metrics,
                      int32_t* h_status, double* h_traj, double* h_aggregate, void* stream);
 
+/* bgr_rollout_host WITHOUT the final synchronise: everything (chunked H2D, kernels, D2H) is queued and the call
+ * returns; the results are valid after bgr_stream_synchronize(stream) (or any later synchronising call on that
+ * stream).  The host buffers must stay alive and untouched until then, and should be pinned (cudaHostAlloc /
+ * torch pin_memory) -- pageable memory makes the copies synchronous.  Consecutive calls from one host thread
+ * pipeline: the first upload of call i + 1 runs under the last kernel and download of call i.  h_traj is not
+ * supported here (BGR_ERR_UNSUPPORTED): a trajectory dump is a debugging aid, not a streaming workload. */
+int bgr_rollout_host_async(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t n_episodes,
+                           const float* h_params, const double* h_init_state, float* h_metrics,
+                           int32_t* h_status, double* h_aggregate, void* stream);
+
 /* ---- one control step for n independent vehicles (the scalar drop-in classes call this with n = 1):
  *      compute_steering (core/controllers.py:193 / :336), curvature lookup (nodes/controller.py:62),
  *      compute_acceleration (:32 / :117), State.update (core/data/car_state.py:118).
@@ -287,7 +306,9 @@ int bgr_rollout_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int
 #define BGR_C_LQG_XHAT0 3
 #define BGR_C_LQG_XHAT1 4
 #define BGR_C_LQG_A_PREV 5
-#define BGR_C_STEP 6         /* LQG: index into the shared Kalman-gain sequence */
+#define BGR_C_STEP 6         /* steps this episode has taken so far: index into the shared Kalman-gain sequence (LQG)
+                                and counter of the observation-noise stream, so that N stepped calls that carry their
+                                controller row draw the same noise as one N-step bgr_rollout */
 #define BGR_C_PREV_STEER 7   /* shadowed Stanley: previous_steering (core/controllers.py:250,319) */
 #define BGR_N_CTRL 8
 /* step output row: double[BGR_N_OUT] */
@@ -312,6 +333,10 @@ int bgr_step_host(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int32_
 /* ---- LQG design shared by all episodes: LQR gain (control.dlqr call, core/controllers.py:97) and the
  *      data-independent Kalman gain sequence (:145,151,154,160).  Host math, no device work. ---- */
 int bgr_lqg_design(double dt, int32_t n_steps, double* h_lqr_gain /*[2]*/, double* h_kf_gains /*[n_steps][2] or NULL*/);
+/* The estimate covariance LQGAccelerationController.P (core/controllers.py:109) after n_steps calls of
+ * kalman_filter_update (:145,:160), row major 2 x 2; n_steps = 0 gives the initial identity.  Same recursion as the
+ * gain sequence above (it is data independent), for callers that inspect ctrl.P. */
+int bgr_lqg_covariance(double dt, int32_t n_steps, double* h_P /*[4]*/);
 
 /* ---- MPC candidate-sequence rollout + cost evaluation: replaces the cvxpy/OSQP solve inside
  *      MPCController.compute_control (core/controllers.py:486-568) by evaluating the reference's own
@@ -319,7 +344,9 @@ int bgr_lqg_design(double dt, int32_t n_steps, double* h_lqr_gain /*[2]*/, doubl
  *      per episode and taking the cheapest feasible (:536) one. ---- */
 int bgr_mpc_eval(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
                  const double* d_state,      /* [n_episodes][4] = x, y, yaw, v */
-                 const int32_t* d_ref_start, /* [n_episodes] first reference waypoint (path[0] of :499-500) */
+                 const int32_t* d_ref_start, /* [n_episodes] first reference waypoint (path[0] of :499-500), in [0, n);
+                                                an out-of-range DEVICE value is wrapped (closed track) or clamped (open),
+                                                bgr_mpc_eval_host rejects it with BGR_ERR_BAD_ARG */
                  const int32_t* d_ref_len,   /* NULL (= path runs to the end of the base lap) or [n_episodes] */
                  const float* d_bank,        /* [K][horizon][2] = (accel, steer) candidate bank */
                  int32_t n_candidates,
@@ -332,6 +359,24 @@ int bgr_mpc_eval_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_
                       const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
                       const float* h_bank, int32_t n_candidates, float* h_best_u, float* h_best_cost,
                       int32_t* h_best_idx, float* h_costs, void* stream);
+
+/* ---- device-resident candidate bank: upload the bank ONCE, score it for many batches of states.  The handle also
+ *      keeps the per-candidate prefix-sum statistics of the factored evaluator for every (dt, R, q_v) it has been used
+ *      with, so a call costs the episode coefficients + the pair scoring only; the host variant then moves 36 B per
+ *      episode in and 16 B out instead of re-sending ~1 MB of bank per call.  The bank's horizon must equal
+ *      cfg->horizon and it must live on the track's device. ---- */
+typedef struct bgr_mpc_bank bgr_mpc_bank_t; /* opaque, device resident */
+int bgr_mpc_bank_create(int device, const float* h_bank /* [K][horizon][2] */, int32_t n_candidates, int32_t horizon,
+                        bgr_mpc_bank_t** out_bank);
+void bgr_mpc_bank_destroy(bgr_mpc_bank_t* bank);
+int bgr_mpc_eval_bank(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                      const double* d_state, const int32_t* d_ref_start, const int32_t* d_ref_len,
+                      bgr_mpc_bank_t* bank, float* d_best_u, float* d_best_cost, int32_t* d_best_idx,
+                      float* d_costs, void* stream);
+int bgr_mpc_eval_bank_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                           const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
+                           bgr_mpc_bank_t* bank, float* h_best_u, float* h_best_cost, int32_t* h_best_idx,
+                           float* h_costs, void* stream);
 
 /* ---- batched system identification: identify_dynamics (old/test_runs_system_id.py:84-111) for every episode of a
  *      trajectory dump: least squares x_{k+1} = A x_k + B u_k + c over the logged rows, x = [x, y, yaw, v, yaw_rate,
@@ -351,6 +396,8 @@ int bgr_identify_dynamics_host(int64_t n_episodes, int32_t max_rows, const doubl
 /* FP32 FMA-chain microbenchmark: the roofline denominator for the step kernels (MEASURED_PEAKS.json has
  * only HBM and bf16).  Returns achieved TFLOP/s (2 flops per FMA) and lane-instructions/s. */
 int bgr_fp32_peak_probe(int device, double* out_tflops, double* out_ginst_per_s);
+/* The same with DFMA chains: the FP64 CUDA-core peak, denominator of the MPC evaluator's roofline. */
+int bgr_fp64_peak_probe(int device, double* out_tflops);
 /* Duration [ms] of the last rollout / mpc kernel launched by this thread on `stream`, measured with
  * CUDA events recorded on that stream around the kernel (synchronises the stream). */
 int bgr_last_kernel_ms(double* out_ms);

@@ -414,6 +414,43 @@ def mpc_costs_batch(x0, y0, yaw0, v0, ref_x, ref_y, bank, dt, WB=CONF.WB,
     return cost, feas
 
 
+def mpc_qp_optimum(x0, y0, yaw0, v0, ref_x, ref_y, H, dt, WB=CONF.WB, target_speed=CONF.TARGET_SPEED,
+                   max_accel=CONF.MAX_ACCEL, max_steer=CONF.MAX_STEER):
+    """The EXACT optimum of the QP that compute_control hands to cvxpy / OSQP (:503-552) -- what the reference's solver
+    approximates to its tolerance (cvxpy 1.x -> OSQP, both absent from the reference tree and from this image: the
+    solver's own iterate stays PARITY UNPINNED; the optimum it converges to is pinned here).
+
+    Under the linearisation x and y do not depend on the controls (:523-524), yaw is driven by the steering only
+    (:525) and v by the acceleration only (:526), and Q, R are diagonal: the QP separates into two bounded
+    least-squares chains of H variables,
+        min_s  sum_{k=0..H} q2 (yaw0 + v0/WB dt sum_{i<k} s_i)^2 + r1 sum_k s_k^2      |s_k| <= MAX_STEER      (:533)
+        min_a  sum_{k=0..H} q3 (v0 - v_t + dt sum_{i<k} a_i)^2  + r0 sum_k a_k^2      |a_k| <= MAX_ACCEL      (:532)
+    (``cp.abs(u[k, 0]) <= MAX_ACCEL``: the QP's acceleration bound is symmetric; MAX_DECEL only enters the final clip,
+    :565), plus v_k >= 0 (:536), which is checked on the solution: if it binds, the v chain is re-solved with SLSQP.
+    Each chain is solved by scipy's bounded-variable least squares (active set: exact up to round-off).
+    Returns (cost, accel (H,), steer (H,))."""
+    from scipy.optimize import lsq_linear, minimize
+    low = np.tril(np.ones((H, H)))                         # row k - 1: sum over i < k, k = 1..H
+
+    def chain(scale, qq, rr, e0, bound):
+        a_mat = np.vstack([math.sqrt(qq) * scale * low, math.sqrt(rr) * np.eye(H)])
+        b_vec = np.concatenate([-math.sqrt(qq) * e0 * np.ones(H), np.zeros(H)])
+        return lsq_linear(a_mat, b_vec, bounds=(-bound, bound), method="bvls", tol=1e-15).x
+
+    steer = chain(v0 / WB * dt, MPC_Q[2], MPC_R[1], yaw0, max_steer)
+    accel = chain(dt, MPC_Q[3], MPC_R[0], v0 - target_speed, max_accel)
+    if np.any(v0 + dt * np.cumsum(accel) < 0.0):           # :536 binds: general inequality constraints
+        def fun(a):
+            e = v0 - target_speed + dt * np.concatenate([[0.0], np.cumsum(a)])
+            return MPC_Q[3] * float(e @ e) + MPC_R[0] * float(a @ a)
+        cons = [{"type": "ineq", "fun": lambda a: v0 + dt * np.cumsum(a)}]
+        res = minimize(fun, np.clip(accel, -max_accel, max_accel), method="SLSQP", bounds=[(-max_accel, max_accel)] * H,
+                       constraints=cons, options={"ftol": 1e-14, "maxiter": 500})
+        accel = res.x
+    cost, _ = mpc_candidate_cost(x0, y0, yaw0, v0, ref_x, ref_y, np.stack([accel, steer], axis=1), dt, WB, target_speed)
+    return float(cost), accel, steer
+
+
 def mpc_select(costs, feasible, bank, max_decel=CONF.MAX_DECEL, max_accel=CONF.MAX_ACCEL,
                max_steer=CONF.MAX_STEER):
     """Pick the cheapest feasible candidate (first minimum wins), then apply the return

@@ -12,7 +12,7 @@ fi
 for v in $variants; do
   lib=""; [ "$v" != base ] && lib="$PWD/bgr_pathplanning_control_b200/libbgr_rollout_$v.so"
   for w in pp_sweep stanley_lqg; do
-    BGR_ROLLOUT_LIB=$lib timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline \
+    BGR_ROLLOUT_LIB=$lib timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-secondary \
       > gpurun_out/bench_${w}_$v.log 2>&1
     echo "bench $w $v rc=$?"; tail -1 gpurun_out/bench_${w}_$v.log | python -c "
 import json,sys
@@ -22,10 +22,11 @@ except Exception as e: print('   (no json)', e)"
   done
 done
 for v in ${NCU_VARIANTS:-base}; do
+  [ "$v" = none ] && continue
   lib=""; [ "$v" != base ] && lib="$PWD/bgr_pathplanning_control_b200/libbgr_rollout_$v.so"
   for w in pp_sweep stanley_lqg; do
     BGR_ROLLOUT_LIB=$lib timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 1 -c 1 \
-      -o gpurun_out/prof_${w}_$v -f python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline \
+      -o gpurun_out/prof_${w}_$v -f python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline --no-secondary \
       > gpurun_out/ncu_${w}_$v.log 2>&1
     echo "ncu $w $v rc=$?"
   done

@@ -1,24 +1,35 @@
 #!/bin/bash
-# One GPU session: parity tests, bench lines, ncu launch list + one full capture of the step kernel.
+# One GPU session (1 x B200): parity tests, the default bench line (config 2 + every other BASELINE config as secondary),
+# the reference arm, then ncu: a launch list of the default command and one `--set full` capture (with source counters)
+# of each kernel DESIGN.md quotes.  Everything lands in gpurun_out/; scripts/make_profiles.sh turns it into profiles/<dir>.
+#   usage: gpurun --timeout 2400 -- bash scripts/gpu_round.sh [notests]
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest.log
+python -c "import bgr_pathplanning_control_b200 as b; print(b.build_id())" > gpurun_out/build_id.txt; cat gpurun_out/build_id.txt
+if [ "$1" != notests ]; then
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --tb=short -rP > gpurun_out/pytest_full.log 2>&1; echo "pytest rc=$?"
+  grep -E "passed|failed|error" gpurun_out/pytest_full.log | tail -3; grep -E "^\[(parity fractions|mpc sub-optimality)" gpurun_out/pytest_full.log
+fi
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks.csv &
 SMI=$!
-timeout 600 python bench.py > gpurun_out/bench_pp.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_pp.log
-timeout 600 python bench.py --workload stanley_lqg --no-cpu-baseline > gpurun_out/bench_stanley.log 2>&1; echo "bench stanley rc=$?"; tail -1 gpurun_out/bench_stanley.log
-timeout 600 python bench.py --workload mpc > gpurun_out/bench_mpc.log 2>&1; echo "bench mpc rc=$?"; tail -1 gpurun_out/bench_mpc.log
-for w in skidpad_mc pp_replan; do timeout 600 python bench.py --workload $w --no-cpu-baseline > gpurun_out/bench_$w.log 2>&1; echo "bench $w rc=$?"; tail -1 gpurun_out/bench_$w.log; done
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "bench ref rc=$?"; tail -1 gpurun_out/bench_ref.log
+timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench default rc=$?"; tail -1 gpurun_out/bench_default.log | cut -c1-300
+for w in pp_replan; do timeout 600 python bench.py --workload $w --no-cpu-baseline > gpurun_out/bench_$w.log 2>&1; echo "bench $w rc=$?"; tail -1 gpurun_out/bench_$w.log | cut -c1-200; done
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "bench ref rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-200
 kill $SMI
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
-$CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 1 -c 1 -o gpurun_out/prof_pp -f $CMD > gpurun_out/ncu_full.log 2>&1
-echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
-CMD2="python bench.py --workload stanley_lqg --steps 2 --warmup 1 --no-cpu-baseline"
-$CMD2 > gpurun_out/plain3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 1 -c 1 -o gpurun_out/prof_stanley -f $CMD2 > gpurun_out/ncu_full2.log 2>&1
-echo "ncu full2 rc=$?"
-ls -la gpurun_out
+cap() {  # <report name> <kernel regex> <skip> <bench args...>
+  name=$1; regex=$2; skip=$3; shift 3
+  python bench.py "$@" --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > gpurun_out/plain_$name.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -o gpurun_out/prof_$name -f \
+    python bench.py "$@" --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > gpurun_out/ncu_$name.log 2>&1
+  echo "ncu $name rc=$?"
+}
+cap pp rollout_kernel 1 --workload pp_sweep
+cap stanley rollout_kernel 1 --workload stanley_lqg
+cap replan rollout_kernel 1 --workload pp_replan
+# config 5: the pure-pursuit kind is the launch that fills the GPU (kinds launch in the order stanley+lqg, stanley+pid, pp)
+cap mc "rollout_kernel_f32.*0.*0.*0.*1" 1 --workload skidpad_mc
+cap mpc mpc_factored_kernel 1 --workload mpc
+ls -la gpurun_out | head -60

@@ -5,8 +5,15 @@ ncu's `--page source --csv` lists executed-instruction counts per SASS instructi
 cubin that ran (the in-tree .o travels to the GPU box unchanged) carries the line table.  Both list the function's
 instructions in address order, so they are joined by position (opcodes are cross-checked).
 
-usage: ncu_lines.py <ncu source csv> <nvdisasm -g listing> <mangled kernel name> <sim steps per launch> [top]
+usage: ncu_lines.py <ncu source csv> <nvdisasm -g listing> <mangled kernel name> <sim steps per launch> [top] [opcodes.json]
+
+With the sixth argument the per-opcode totals are also written as JSON, together with the EXECUTED fp32 arithmetic of
+the kernel: warp-instructions per warp-step on the FMA pipe's arithmetic opcodes and the flops per lane-step they
+stand for (FADD / FMUL = 1, FFMA = 2; packed FADD2 / FMUL2 = 2, FFMA2 = 4).  ncu's own
+smsp__sass_thread_inst_executed_op_f{add,mul,fma} counters do not see the packed opcodes, so bench.py takes its
+``executed_fp32_frac`` from this table.
 """
+import json
 import collections
 import csv
 import re
@@ -14,6 +21,9 @@ import sys
 
 src_csv, listing, kernel, steps = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 60
+ops_json = sys.argv[6] if len(sys.argv) > 6 else None
+if steps <= 0:
+    steps = 32.0          # no unit count known: the table is then in warp-instructions per launch
 
 rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
@@ -57,6 +67,17 @@ for (loc, text), (n, _) in zip(ins, ncu):
     per_line_ops[loc][opcode(text)] += n / W
 total = sum(per_line.values())
 print(f"TOTAL warp-instructions per warp-step: {total:.2f}")
+if ops_json:
+    by_op = collections.Counter()
+    for (loc, text), (n, _) in zip(ins, ncu):
+        by_op[opcode(text)] += n / W
+    flops = {"FADD": 1, "FMUL": 1, "FFMA": 2, "FADD2": 2, "FMUL2": 2, "FFMA2": 4}
+    json.dump({"kernel": kernel, "units_per_launch": steps, "warp_inst_per_warp_step": total,
+               "by_opcode": {k: round(v, 4) for k, v in by_op.most_common()},
+               "fp32_warp_inst_per_warp_step": sum(by_op[k] for k in flops),
+               "fp32_flops_per_lane_step": sum(by_op[k] * f for k, f in flops.items()),
+               "counting": "FADD/FMUL 1, FFMA 2, FADD2/FMUL2 2, FFMA2 4 flops per lane; compares, min/max, conversions, MUFU not counted"},
+              open(ops_json, "w"), indent=1)
 for loc, v in per_line.most_common(top):
     ops = " ".join(f"{k}:{x:.1f}" for k, x in per_line_ops[loc].most_common(6))
     print(f"{v:7.2f}  {loc[0]}:{loc[1]:<5d} {ops}")

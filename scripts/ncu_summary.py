@@ -45,7 +45,7 @@ def main():
                     d[k] = {"value": float(vals[i].replace(",", "")), "unit": units[i]}
                 except ValueError:
                     d[k] = {"value": vals[i], "unit": units[i]}
-        if len(sys.argv) > 2:
+        if len(sys.argv) > 2 and float(sys.argv[2]) > 0:
             steps = float(sys.argv[2])
             inst = d["smsp__inst_executed.sum"]["value"]
             d["derived"] = {"sim_steps_per_launch": steps, "warp_inst_per_warp_step": inst / (steps / 32.0)}

@@ -1,10 +1,10 @@
 #!/bin/bash
-# 1 -> 8 GPU weak-scaling of the bench on ONE 8-GPU box (run with: gpurun --gpus 8 -- bash scripts/scaling_round.sh)
+# Multi-GPU check of the default bench command on ONE box: gpurun --gpus N -- bash scripts/scaling_round.sh "1 2"
+# (each N runs the full default line: config 2 headline + configs 3 weak / 3 strong / 4 / 5 as secondary)
 mkdir -p gpurun_out
-run() {  # n workload
-  if [ "$1" = 1 ]; then timeout 600 python bench.py --gpus 1 --workload $2 --no-cpu-baseline
-  else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $1 --workload $2 --no-cpu-baseline
-  fi
-}
-for n in 1 2 4 8; do run $n pp_sweep 2>gpurun_out/scale_pp_$n.err | tail -1 > gpurun_out/scale_pp_$n.json; echo "pp N=$n rc=$?"; cut -c1-220 gpurun_out/scale_pp_$n.json; done
-for n in 8; do run $n stanley_lqg 2>gpurun_out/scale_stanley_$n.err | tail -1 > gpurun_out/scale_stanley_$n.json; echo "stanley N=$n rc=$?"; cut -c1-220 gpurun_out/scale_stanley_$n.json; done
+for n in ${1:-1 2}; do
+  if [ "$n" = 1 ]; then timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline
+  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline
+  fi 2> gpurun_out/scale_$n.err | tail -1 > gpurun_out/scale_$n.json
+  echo "N=$n rc=$?"; cut -c1-260 gpurun_out/scale_$n.json; tail -3 gpurun_out/scale_$n.err
+done

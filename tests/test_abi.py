@@ -133,6 +133,41 @@ def test_lqg_design_is_host_math_and_matches_the_reference_gain():
     assert g.shape == (50, 2) and np.all(g[:, 0] > 0) and np.all(g[:, 0] < 1)
 
 
+def test_lqg_controller_exposes_the_reference_instance_attributes():
+    """anything that inspects ``ctrl.A / B / C / Q / R / K / Q_kf / R_kf / P`` (core/controllers.py:83-109)
+    must find them; ``P`` follows the covariance recursion of kalman_filter_update (:145, :160), one update per
+    compute_acceleration call (:126).  Host math behind the ABI (bgr_lqg_covariance): no GPU needed."""
+    dt = 0.05
+    A = np.array([[1, 0], [dt, 1]]); Cm = np.array([[1, 0]])                       # noqa: E702  (:83-87)
+    Qk, Rk = np.diag([0.1, 0.1]), np.array([[0.5]])                                 # :101-104
+    P = np.eye(2)                                                                   # :109
+    np.testing.assert_array_equal(bgr.lqg_covariance(dt, 0), P)
+    for n in range(1, 40):
+        P_pred = A @ P @ A.T + Qk                                                   # :145
+        S = Cm @ P_pred @ Cm.T + Rk                                                 # :151
+        K_kf = P_pred @ Cm.T @ np.linalg.inv(S)                                     # :154
+        P = (np.eye(2) - K_kf @ Cm) @ P_pred                                        # :160
+        np.testing.assert_allclose(bgr.lqg_covariance(dt, n), P, rtol=1e-13, atol=1e-15)
+    ctl = bgr.LQGAccelerationController(dt)                # (constructor: host math only, no device call)
+    np.testing.assert_array_equal(ctl.A, A)
+    np.testing.assert_array_equal(ctl.B, [[dt], [0]])
+    np.testing.assert_array_equal(ctl.C, Cm)
+    np.testing.assert_array_equal(ctl.Q, np.diag([10.0, 100.0]))
+    np.testing.assert_array_equal(ctl.R, [[0.001]])
+    np.testing.assert_array_equal(ctl.Q_kf, Qk)
+    np.testing.assert_array_equal(ctl.R_kf, Rk)
+    assert ctl.K.shape == (1, 2) and ctl.x_hat.shape == (2, 1) and ctl.a_k_prev == 0.0 and ctl.v_desired == 0.0
+    np.testing.assert_array_equal(ctl.P, np.eye(2))        # before the first call
+    with pytest.raises(RuntimeError):
+        bgr.lqg_covariance(-1.0, 3)
+
+
+def test_build_id_names_this_build():
+    """bench.py quotes ncu evidence only for the build id it was captured from (profiles/<dir>/build_id.txt)."""
+    bid = bgr.build_id()
+    assert isinstance(bid, str) and len(bid) >= 16 and bid != "unknown"
+
+
 def test_no_cpu_fallback_without_a_device():
     """On a machine without CUDA every compute entry point fails loudly."""
     import torch

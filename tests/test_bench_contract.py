@@ -42,7 +42,7 @@ def test_reference_arm_other_ranks_exit_quietly():
 @pytest.mark.parametrize("workload", ["pp_sweep", "stanley_lqg", "mpc", "skidpad_mc", "pp_replan"])
 def test_gpu_arm_json_line(workload):
     d = run_bench("--workload", workload, "--steps", "3", "--warmup", "3", "--episodes", "16384", "--sim-steps", "300",
-                  "--cpu-seconds", "1")
+                  "--cpu-seconds", "1", "--no-secondary")
     assert BASE_KEYS | {"roofline", "gpu_launches", "clocks"} <= set(d) or workload == "mpc"
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3
     assert d["gpu_launches"] >= 3
@@ -54,3 +54,23 @@ def test_gpu_arm_json_line(workload):
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
         assert d["clocks"]["sm_max_mhz"] and d["roofline"]["hbm"]["peak"] > 1000
         assert d["config"]["episodes_per_gpu"] == 16384
+
+
+@pytest.mark.gpu
+def test_default_run_carries_every_baseline_config():
+    """The driver only ever runs ``bench.py --gpus N --steps K --warmup W``: that ONE line must carry BASELINE configs
+    3 (weak and 4x-episodes strong), 4 and 5 as secondary records with value / e2e / roofline / clocks each."""
+    d = run_bench("--steps", "3", "--warmup", "3", "--episodes", "16384", "--sim-steps", "300", "--no-cpu-baseline")
+    assert d["config"]["workload"].startswith("config 2") and d["e2e"]["frac_of_value"] > 0
+    assert d["roofline"]["ncu"]["matches_loaded_library"] in (True, False)
+    if not d["roofline"]["ncu"]["matches_loaded_library"]:
+        assert d["roofline"]["issue"] is None and d["roofline"]["ncu"]["stale"] is True
+    sec = d["secondary"]
+    assert set(sec) == {"config3_weak", "config3_strong", "config4_mpc", "config5_skidpad_mc"}
+    for name, r in sec.items():
+        assert "error" not in r, (name, r)
+        assert r["value"] > 0 and r["e2e"]["value"] > 0 and r["roofline"]["frac"] > 0 and "clocks" in r, name
+    assert sec["config3_strong"]["scaling"] == "strong" and sec["config3_strong"]["config"]["episodes_total"] == 4 * 16384
+    assert sec["config4_mpc"]["roofline"]["bound"] == "fp64" and sec["config4_mpc"]["one_call_per_step"]["value"] > 0
+    assert sec["config4_mpc"]["dtype"].startswith("f64")
+

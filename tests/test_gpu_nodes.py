@@ -37,12 +37,14 @@ def test_controller_node_update_protocol(cuda_device):
                                 a_angular=Obj(x_val=0.1, y_val=0.2), a_linear=Obj(x_val=0.3, y_val=0.4),
                                 timestamp=0.05 * k)
         data["current_time"] = 0.05 * k
+        data["target_ind"] = ti             # what a Planner node would have published (nodes/planner.py:101)
         node.update(data)
+        assert data["target_ind"] == ti     # ... and the controller leaves it alone, like the reference's
         want_s, ti = laws.pure_pursuit_steering(state[0], state[1], state[2], cx, cy, ti, bgr.conf.LOOKAHEAD_DISTANCE)
         kap = curve[ti] if ti < len(curve) else curve[-1]
         want_a, want_v = laws.pid_acceleration(pid, state[3], kap, bgr.conf.kp_accel, bgr.conf.ki_accel,
                                                bgr.conf.kd_accel, bgr.conf.dt)
-        assert data["target_ind"] == ti
+        assert node.target_ind == ti
         assert abs(data["steering"] - want_s) < 1e-12 and abs(data["acceleration"] - want_a) < 1e-11
         assert abs(data["v_log"] - want_v) < 1e-12
         assert sent[-1] == (-data["steering"], data["acceleration"])              # sign flip on the way out (:90)

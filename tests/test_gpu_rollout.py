@@ -596,3 +596,71 @@ def test_rollout_groups_from_host_buffers(cuda_device):
     for a, b in zip(one, many):
         assert np.array_equal(a.status, b.status) and np.array_equal(a.metrics.view(np.int32), b.metrics.view(np.int32))
         assert np.array_equal(a.aggregate, b.aggregate)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_stepped_closed_loop_with_noise_equals_one_rollout(cuda_device, precision):
+    """N calls of bgr_step_host that carry their controller row draw the SAME observation noise as one
+    N-step bgr_rollout (the Philox counter is the episode's own step count, BGR_C_STEP), so a stepped closed loop
+    reproduces the rollout: bit for bit in the fp64 build, to rounding in the fp32 build (whose in-kernel state is a
+    double-float pair that a stepped caller re-splits from fp64 every call)."""
+    import ctypes as C
+    ta = bgr.tracks.skidpad(512)
+    track = bgr.Track.from_arrays(ta, cone_reach=4.0)
+    N, E = 60, 3
+    noise = dict(sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1, noise_seed=99, episode_id_base=1000)
+    cfg = bgr.RolloutConfig(steer="stanley", accel="lqg", model="kinematic", precision=precision, max_steps=N, **noise)
+    params = bgr.default_params(E)
+    init = bgr.initial_states(ta, E, index=0, v0=3.0)
+    init[:, abi.YAW] = 0.0
+    init[:, abi.Y] += [0.0, 0.1, -0.1]
+    want = bgr.rollout(track, cfg, params, init, traj=True).traj
+    lib = abi.load()
+    state = init.copy()
+    ctrl = np.zeros((E, abi.N_CTRL))
+    ti = np.zeros(E, np.int32)
+    p64 = params.astype(np.float64)
+    out = np.zeros((E, abi.N_OUT))
+    c = cfg.to_struct()
+    phases = abi.PHASE_STEER | abi.PHASE_ACCEL | abi.PHASE_MODEL | abi.PHASE_ERRORS
+    steer = np.empty((N, E))
+    xs = np.empty((N, E))
+    for k in range(N):
+        xs[k] = state[:, abi.X]
+        abi.check(lib.bgr_step_host(track.handle, C.byref(c), phases, E, p64.ctypes.data, state.ctypes.data,
+                                    ti.ctypes.data, ctrl.ctypes.data, None, out.ctypes.data, None))
+        steer[k] = out[:, abi.O_STEER]
+        assert np.all(ctrl[:, abi.C_STEP] == k + 1)
+    if precision == "fp64":
+        assert np.array_equal(steer, want[:, :, abi.T_STEER].T)
+        assert np.array_equal(xs, want[:, :, abi.T_X].T)
+    else:
+        assert np.abs(steer - want[:, :, abi.T_STEER].T).max() < 1e-4
+        assert np.abs(xs - want[:, :, abi.T_X].T).max() < 1e-4
+    # the noise is white, not a constant bias: the per-step steering differs from the noise-free run by varying amounts
+    clean = bgr.rollout(track, bgr.RolloutConfig(steer="stanley", accel="lqg", model="kinematic", precision=precision,
+                                                 max_steps=N), params, init, traj=True).traj
+    d = want[0, :, abi.T_STEER] - clean[0, :, abi.T_STEER]
+    assert np.std(np.diff(d[:20])) > 1e-4
+
+
+def test_async_host_rollouts_pipeline_and_equal_the_synchronous_call(oval, cuda_device):
+    """bgr_rollout_host_async: several batches in flight, each completing on its own stream; every result equals
+    the synchronous bgr_rollout_host call bit for bit (the graded chunk schedule changes nothing but timing)."""
+    import torch
+    ta, track = oval
+    cfg = bgr.RolloutConfig(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=200, laps=2)
+    sizes = [70001, 300, 131072 + 513, 1]
+    jobs = []
+    for i, E in enumerate(sizes):
+        params = torch.from_numpy(bgr.sweeps.pp_sweep_params(E, start=1000 * i)).pin_memory().numpy()
+        init = torch.from_numpy(bgr.initial_states(ta, E, lateral_offset=np.linspace(-0.1, 0.1, E))).pin_memory().numpy()
+        jobs.append((params, init))
+    pend = [bgr.rollout_async(track, cfg, p, s, aggregate=True) for p, s in jobs]
+    got = [h.wait() for h in pend]
+    for (p, s), g, E in zip(jobs, got, sizes):
+        ref = bgr.rollout(track, cfg, p, s, aggregate=True)
+        assert np.array_equal(g.metrics, ref.metrics) and np.array_equal(g.status, ref.status)
+        assert np.array_equal(g.aggregate, ref.aggregate) and g.aggregate[abi.A_EPISODES] == E
+        assert pend[0].wait() is got[0]          # wait() is idempotent
+

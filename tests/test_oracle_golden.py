@@ -301,3 +301,45 @@ def test_replanning_regime_matches_reference_nodes(name):
     # controller look-ahead it holds a path for several ticks
     replans = np.diff([0] + g["replans"])
     assert replans.max() == 1 and (replans.min() == 1) == (name == "ellipse_h40_s3")
+
+
+def test_mpc_qp_optimum_is_the_minimum_of_the_reference_cost():
+    """oracle ``mpc_qp_optimum``: the exact optimum of the QP core/controllers.py:503-552 builds (two bounded
+    least-squares chains).  Checked from first principles: it is feasible, no candidate of either bank and no
+    feasible perturbation of it is cheaper under the cost the golden vectors pin (``mpc_candidate_cost``), and the
+    v >= 0 constraint (:536) is honoured when it binds."""
+    import bgr_pathplanning_control_b200 as bgr
+    C = laws.CONF
+    H, dt = 30, 0.05
+    cx, cy = ellipse(720, 40.0, 20.0)
+    rng = np.random.default_rng(7)
+    banks = [bgr.candidate_bank(512, H).astype(np.float64),
+             bgr.candidate_bank(1024, H, kind="qp_family").astype(np.float64)]
+    for case in range(12):
+        i = int(rng.integers(0, 720))
+        x0, y0 = cx[i] + rng.normal(0, 0.3), cy[i] + rng.normal(0, 0.3)
+        yaw0, v0 = float(rng.uniform(-3.2, 3.2)), float(rng.uniform(0.0, 9.0))
+        ref = (i + np.arange(H)) % 720
+        J, a, s_ = laws.mpc_qp_optimum(x0, y0, yaw0, v0, cx[ref], cy[ref], H, dt)
+        assert np.all(np.abs(a) <= C.MAX_ACCEL + 1e-12) and np.all(np.abs(s_) <= C.MAX_STEER + 1e-12)
+        assert np.all(v0 + dt * np.cumsum(a) >= -1e-12)
+        for bank in banks:
+            c, f = laws.mpc_costs_batch(x0, y0, yaw0, v0, cx[ref], cy[ref], bank, dt)
+            assert np.all(c[f] >= J * (1 - 1e-9) - 1e-9)
+        u = np.stack([a, s_], axis=1)
+        for _ in range(200):                       # feasible perturbations never lower the cost (convexity + optimality)
+            du = rng.normal(0, 0.05, u.shape)
+            w = np.clip(u + du, [-C.MAX_ACCEL, -C.MAX_STEER], [C.MAX_ACCEL, C.MAX_STEER])
+            cw, fw = laws.mpc_candidate_cost(x0, y0, yaw0, v0, cx[ref], cy[ref], w, dt)
+            assert (not fw) or cw >= J * (1 - 1e-9) - 1e-9
+    # the qp_family bank contains the optimum up to its grid: within 0.5 % here (0.2 % over config 4's states)
+    J, _, _ = laws.mpc_qp_optimum(40.0, 0.2, 1.4, 4.0, cx[:H], cy[:H], H, dt)
+    c, f = laws.mpc_costs_batch(40.0, 0.2, 1.4, 4.0, cx[:H], cy[:H], bgr.candidate_bank(4096, H, kind="qp_family"), dt)
+    assert 0.0 <= c[f].min() / J - 1.0 < 5e-3
+    # :536 binding: a target speed below zero pulls v through 0; the optimum stops AT 0 and beats every feasible candidate
+    J, a, s_ = laws.mpc_qp_optimum(0.0, 0.0, 0.1, 0.3, cx[:H], cy[:H], H, dt, target_speed=-2.0)
+    v = 0.3 + dt * np.cumsum(a)
+    assert v.min() >= -1e-9 and v.min() < 1e-6
+    c, f = laws.mpc_costs_batch(0.0, 0.0, 0.1, 0.3, cx[:H], cy[:H], banks[0], dt, target_speed=-2.0)
+    assert f.any() and np.all(c[f] >= J * (1 - 1e-7))
+

@@ -57,8 +57,15 @@ def _worker(rank, world, port, E, q):
     try:
         lo, hi = sharding.shard_range(E, rank, world)
         m, s, agg = _fake_block(lo, hi)
-        M, S, A = sharding.gather_results(torch.from_numpy(m), torch.from_numpy(s), torch.from_numpy(agg), E)
-        q.put((rank, M.numpy(), S.numpy(), A.numpy()))
+        tm, ts, ta = torch.from_numpy(m), torch.from_numpy(s), torch.from_numpy(agg)
+        M, S, A = sharding.gather_results(tm, ts, ta, E)                       # gather to rank 0 + reduce
+        Ma, Sa, Aa = sharding.gather_results(tm, ts, ta, E, dst=None)          # all-gather variant
+        _, _, Ar = sharding.gather_results(tm, ts, ta, E, rows=False)          # reduce only
+        assert (M is None) == (rank != 0) and (S is None) == (rank != 0)
+        assert torch.equal(A, Aa) and torch.equal(A, Ar)
+        if rank == 0:
+            assert torch.equal(M, Ma) and torch.equal(S, Sa)
+        q.put((rank, Ma.numpy(), Sa.numpy(), A.numpy()))
     finally:
         dist.destroy_process_group()
 
