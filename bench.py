@@ -791,7 +791,8 @@ def run_mpc(ctx, steps, warmup, E=16384, K=4096, H=30):
     value = units_step * world / (ms * 1e-3)
     return {
         "metric": "MPC candidate-steps/sec (episodes x candidates x horizon)", "value": value,
-        "unit": "candidate-steps/s", "n_gpus": world, "steps": n_rep if graph is not None else n_call, "warmup": warmup,
+        "unit": "candidate-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "timed_evaluations": n_rep if graph is not None else n_call,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": dtype, "data": "synthetic",
         "config": {"workload": "config 4: MPC candidate-sequence rollout/cost evaluation, 16384 episodes x 4096 "

@@ -79,7 +79,7 @@ class TrackInfo(C.Structure):
                 ("smem_bytes_fp32", C.c_int64), ("smem_bytes_fp64", C.c_int64),
                 ("guard_min", C.c_double), ("guard_median", C.c_double), ("ds_min", C.c_double),
                 ("ds_max", C.c_double), ("rival_total", C.c_int64), ("rival_max", C.c_int32),
-                ("rival_unlisted", C.c_int32)]
+                ("rival_unlisted", C.c_int32), ("twin_count", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RolloutCfg(C.Structure):

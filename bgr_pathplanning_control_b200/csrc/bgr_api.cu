@@ -154,10 +154,18 @@ static void kalman_gains_host(double dt, int n_steps, double* out /*[n][2] or nu
 // argmin is the best of {j} U rivals(j) -- a handful of evaluations instead of a scan over all n waypoints.
 constexpr int kMaxRivals = 1024;   // longer lists fall back to the exact scan (a list is still cheaper than 32 scans)
 
+// Twin triples: on a track that drives the same line twice (skidpad circles) the closest rival of waypoint j is always
+// its twin t(j) on the other lap or one of t's index neighbours, while every OTHER waypoint needs the car to be metres
+// away before it can win.  twin[j] = (t, squared guard_twin) with guard_twin(j) = the smallest reach-in distance over all
+// waypoints outside {j - 1, j, j + 1} U {t - 1, t, t + 1} (cyclic indices, as the kernels' padded table reads them):
+// for p in slab(j) with |p - w_j| < guard_twin(j) the exact argmin is the best of j and the twin triple -- three
+// evaluations from shared memory instead of a walk through the sorted rival list.  Same exactness argument as the
+// guard itself (only the excluded set is larger, and it is evaluated exhaustively).
 static void compute_guards(const std::vector<double>& x, const std::vector<double>& y, bool closed,
                            std::vector<double>* guard, std::vector<int32_t>* rival_first,
-                           std::vector<int2>* rival_list) {
+                           std::vector<int2>* rival_list, std::vector<int2>* twin) {
   const int n = static_cast<int>(x.size());
+  twin->assign(n, make_int2(-1, 0));
   guard->assign(n, 0.0);
   rival_first->assign(n + 1, 0);
   rival_list->clear();
@@ -225,6 +233,21 @@ static void compute_guards(const std::vector<double>& x, const std::vector<doubl
       // sorted by the distance from w_j at which the rival can first win: the device walks a list only up to the
       // car's own distance from w_j (stored 1e-4 m short, which covers the fp32 rounding of waypoints and offsets)
       std::sort(mine.begin(), mine.end());
+      if (!mine.empty() && n >= 8) {
+        const int t = mine.front().second;
+        double gt2 = reach2;                       // everything not listed needs at least the lists' reach
+        for (const auto& m : mine) {
+          const int di = ((m.second - t) % n + n) % n;
+          if (di == 0 || di == 1 || di == n - 1) continue;     // the twin triple itself (cyclic)
+          gt2 = std::min(gt2, m.first);
+          break;                                               // sorted: the first one outside the triple is the minimum
+        }
+        // the triple must not overlap j's own neighbourhood in a way the index tie rule could not see: it may (the
+        // kernel compares true indices); shrink like the guard: 1e-4 relative + 1e-4 m
+        const double g = std::max(0.0, std::sqrt(gt2) * (1.0 - 1e-4) - 1e-4);
+        const float g2f = std::nextafterf(static_cast<float>(g * g), 0.0f);
+        if (g2f > 0.0f) (*twin)[j] = make_int2(t, __builtin_bit_cast(int, g2f));
+      }
       for (const auto& m : mine) {
         const double c = std::max(0.0, std::sqrt(m.first) - 1e-4);
         const float c2 = std::nextafterf(static_cast<float>(c * c), 0.0f);
@@ -350,6 +373,7 @@ extern "C" void bgr_track_destroy(bgr_track_t* t) {
   cudaFree(t->guard2);
   cudaFree(t->rival_range);
   cudaFree(t->rival_list);
+  cudaFree(t->twin);
   cudaFree(t->cone_range);
   cudaFree(t->cone_near);
   cudaFree(t->cone_list);
@@ -435,7 +459,9 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   }
   std::vector<int32_t> rival_first;
   std::vector<int2> rival_list;
-  compute_guards(t->x, t->y, t->closed != 0, &t->guard_radius, &rival_first, &rival_list);
+  std::vector<int2> twin;
+  compute_guards(t->x, t->y, t->closed != 0, &t->guard_radius, &rival_first, &rival_list, &twin);
+  for (const auto& tw : twin) t->twin_count += tw.x >= 0 ? 1 : 0;
 
   t->ds_min = INFINITY;
   t->ds_max = 0.0;
@@ -529,6 +555,7 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   if (rc == BGR_OK) rc = upload(&t->guard2, guard2);
   if (rc == BGR_OK) rc = upload(&t->rival_range, rival_range);
   if (rc == BGR_OK) rc = upload(&t->rival_list, rival_list);
+  if (rc == BGR_OK) rc = upload(&t->twin, twin);
   if (rc == BGR_OK && t->n_cones > 0) {
     rc = upload(&t->cone_range, cone_range);
     if (rc == BGR_OK) rc = upload(&t->cone_near, cone_near);
@@ -562,6 +589,7 @@ extern "C" int bgr_track_info(const bgr_track_t* t, bgr_track_info_t* out) {
   out->rival_total = t->rival_total;
   out->rival_max = t->rival_max;
   out->rival_unlisted = t->rival_unlisted;
+  out->twin_count = t->twin_count;
   return BGR_OK;
 }
 
@@ -593,7 +621,7 @@ struct StepPlumbing {
   bool force_full = false;
 };
 
-using LaunchFn = cudaError_t (*)(const RolloutArgs&, int, size_t, int, cudaStream_t);
+using LaunchFn = cudaError_t (*)(const RolloutArgs&, int, size_t, int, cudaStream_t, int*);
 
 template <typename Real, bool EXTRAS>
 LaunchFn pick(int s, int a, int m) {
@@ -660,6 +688,7 @@ struct Plan {
   LaunchFn fn = nullptr;
   size_t smem = 0;
   int smem_optin = 0;   // the device's opt-in shared-memory maximum (per-function attribute of every step kernel)
+  long long wave = 0;   // episodes the device runs at once with this kernel (SMs x resident CTAs x threads)
 };
 
 // Validate the configuration, fill the kernel arguments that do not depend on the episode range, pick the kernel
@@ -808,6 +837,10 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   else if (full) plan->fn = pick<float, true>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
   else plan->fn = pick<float, false>(cfg->steer_kind, cfg->accel_kind, cfg->model_kind);
   (void)stream;
+  // how many episodes the device holds at once with this kernel (occupancy query through the launcher)
+  int resident = 0;
+  BGR_CUDA(plan->fn(A, 0, plan->smem, plan->smem_optin, nullptr, &resident));
+  plan->wave = static_cast<long long>(di.sm_count) * std::max(resident, kRolloutThreads);
   return BGR_OK;
 }
 
@@ -831,7 +864,7 @@ int launch_range(const Plan& plan, long long id_offset, long long count, const f
   A.idx = d_idx;
   A.count = d_count;
   const int grid = static_cast<int>((count + kRolloutThreads - 1) / kRolloutThreads);
-  cudaError_t err = plan.fn(A, grid, plan.smem, plan.smem_optin, stream);
+  cudaError_t err = plan.fn(A, grid, plan.smem, plan.smem_optin, stream, nullptr);
   if (err == cudaSuccess) count_launch();
   return check_cuda(err, "rollout kernel launch");
 }
@@ -988,72 +1021,144 @@ struct DeviceScope {
 
 namespace {
 
-// Two internal streams + events per host thread and device: bgr_rollout_host pipelines the H2D copy of chunk c + 1
-// and the D2H copy of chunk c - 1 under the kernel of chunk c.
+// The host-buffer pipeline of bgr_rollout_host / bgr_rollout_host_async, per host thread:
+//   * one UPLOAD stream, two COMPUTE streams, one DOWNLOAD stream, tied together by events.  Uploads of all chunks are
+//     queued back to back (nothing but PCIe paces them), chunk c's kernel waits for its own upload only, its download
+//     waits for its own kernel only: no copy ever sits between two kernels of the same stream.
+//   * chunks are sized in WAVES.  Every CTA of a rollout runs the full episode length, so a chunk kernel lasts one CTA
+//     lifetime whatever its size: a chunk that does not fill the machine wastes the rest of it for that long.  The
+//     first wave is split 1/4 + 3/4 over the two compute streams (the first kernel starts after a quarter of the first
+//     wave's upload), then whole waves follow; kernels of consecutive chunks overlap at their edges because they
+//     alternate between the two compute streams.
+//   * device buffers live in a small ring of SLOTS that persist across calls (grown on demand, never shrunk): no
+//     stream-ordered allocation per call, whose cross-stream reuse would serialise consecutive asynchronous calls, and
+//     up to kSlots calls in flight per thread (bgr_rollout_host_async).
+constexpr int kSlots = 3;
+struct Slot {
+  size_t cap = 0, cap_partials = 0, cap_work = 0;   // capacities in episodes / rows / ints
+  float* d_params = nullptr;
+  double* d_init = nullptr;
+  float* d_metrics = nullptr;
+  int32_t* d_status = nullptr;
+  double* d_partials = nullptr;
+  double* d_agg = nullptr;
+  int32_t* d_work = nullptr;
+  cudaEvent_t done = nullptr;
+  bool used = false;
+};
 struct Pipeline {
   int device = -1;
-  cudaStream_t s[2] = {nullptr, nullptr};
-  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaStream_t up = nullptr, down = nullptr, comp[2] = {nullptr, nullptr};
   cudaEvent_t ready = nullptr;
+  std::vector<cudaEvent_t> ev;   // [2 c] = upload of chunk c done, [2 c + 1] = kernel of chunk c done (re-recorded per call)
+  Slot slot[kSlots];
+  unsigned next = 0;
+  ~Pipeline() { release(); }
+  void release() {
+    if (device < 0) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    for (cudaStream_t st : {up, down, comp[0], comp[1]})
+      if (st != nullptr) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+      }
+    if (ready != nullptr) cudaEventDestroy(ready);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+    for (Slot& sl : slot) {
+      cudaFree(sl.d_params); cudaFree(sl.d_init); cudaFree(sl.d_metrics); cudaFree(sl.d_status);
+      cudaFree(sl.d_partials); cudaFree(sl.d_agg); cudaFree(sl.d_work);
+      if (sl.done != nullptr) cudaEventDestroy(sl.done);
+      sl = Slot();
+    }
+    up = down = comp[0] = comp[1] = nullptr;
+    ready = nullptr;
+    cudaSetDevice(prev);
+    device = -1;
+  }
 };
 thread_local Pipeline g_pipe;
 
 int ensure_pipeline(int device) {
   if (g_pipe.device == device) return BGR_OK;
-  if (g_pipe.device >= 0) {
-    for (int i = 0; i < 2; ++i) {
-      cudaStreamDestroy(g_pipe.s[i]);
-      cudaEventDestroy(g_pipe.done[i]);
-    }
-    cudaEventDestroy(g_pipe.ready);
-    g_pipe.device = -1;
-  }
-  for (int i = 0; i < 2; ++i) {
-    BGR_CUDA(cudaStreamCreateWithFlags(&g_pipe.s[i], cudaStreamNonBlocking));
-    BGR_CUDA(cudaEventCreateWithFlags(&g_pipe.done[i], cudaEventDisableTiming));
-  }
+  g_pipe.release();
+  BGR_CUDA(cudaStreamCreateWithFlags(&g_pipe.up, cudaStreamNonBlocking));
+  BGR_CUDA(cudaStreamCreateWithFlags(&g_pipe.down, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) BGR_CUDA(cudaStreamCreateWithFlags(&g_pipe.comp[i], cudaStreamNonBlocking));
   BGR_CUDA(cudaEventCreateWithFlags(&g_pipe.ready, cudaEventDisableTiming));
+  for (Slot& sl : g_pipe.slot) BGR_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   g_pipe.device = device;
   return BGR_OK;
 }
 
-// episodes per pipelined chunk (a multiple of the CTA size; BGR_HOST_CHUNK overrides it for tuning)
-long long host_chunk() {
-  static const long long v = [] {
-    long long c = 1 << 17;
-    if (const char* e = std::getenv("BGR_HOST_CHUNK")) {
-      const long long x = std::atoll(e);
-      if (x >= kRolloutThreads) c = x / kRolloutThreads * kRolloutThreads;
-    }
-    return c;
-  }();
-  return v;
+int ensure_chunk_events(size_t n_chunks) {
+  while (g_pipe.ev.size() < 2 * n_chunks) {
+    cudaEvent_t e;
+    BGR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_pipe.ev.push_back(e);
+  }
+  return BGR_OK;
 }
 
-}  // namespace
+template <typename T>
+int grow(T** p, size_t count) {
+  cudaFree(*p);
+  *p = nullptr;
+  BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return BGR_OK;
+}
 
-namespace {
+// the next slot of the ring, free of its previous user and large enough for this call
+int acquire_slot(size_t E, size_t n_partials, size_t n_work, Slot** out) {
+  Slot& sl = g_pipe.slot[g_pipe.next++ % kSlots];
+  if (sl.used) BGR_CUDA(cudaEventSynchronize(sl.done));
+  if (sl.cap < E) {
+    const size_t cap = E + E / 8;
+    BGR_TRY(grow(&sl.d_params, cap * BGR_N_PARAMS));
+    BGR_TRY(grow(&sl.d_init, cap * BGR_N_STATE));
+    BGR_TRY(grow(&sl.d_metrics, cap * BGR_N_METRICS));
+    BGR_TRY(grow(&sl.d_status, cap * BGR_N_STATUS));
+    sl.cap = cap;
+  }
+  if (sl.cap_partials < n_partials) {
+    BGR_TRY(grow(&sl.d_partials, (n_partials + n_partials / 8 + 8) * BGR_N_AGG));
+    sl.cap_partials = n_partials + n_partials / 8 + 8;
+  }
+  if (sl.d_agg == nullptr) BGR_TRY(grow(&sl.d_agg, BGR_N_AGG));
+  if (sl.cap_work < n_work) {
+    BGR_TRY(grow(&sl.d_work, n_work + n_work / 8 + 64));
+    sl.cap_work = n_work + n_work / 8 + 64;
+  }
+  sl.used = true;
+  *out = &sl;
+  return BGR_OK;
+}
 
-// Chunk sizes of the host-buffer pipeline: full chunks in the middle, a short ramp (1/8, 1/4, 1/2 of a chunk) at both
-// ends.  The first upload and the last download of a call are the only copies nothing can hide; short end chunks make
-// them short, and their small kernels share the GPU with their neighbours on the other internal stream.
-std::vector<long long> host_chunks(long long n_episodes) {
-  const long long C = host_chunk();
-  std::vector<long long> head, tail, out;
+// Chunk sizes (episodes) for n episodes on a machine that holds `wave` of them at once.  BGR_HOST_CHUNK=<episodes>
+// overrides the wave size for tuning.
+std::vector<long long> host_chunks(long long n_episodes, long long wave) {
+  static const long long forced = [] {
+    const char* e = std::getenv("BGR_HOST_CHUNK");
+    return e != nullptr ? std::atoll(e) : 0LL;
+  }();
+  if (forced >= kRolloutThreads) wave = forced;
+  wave = std::max<long long>(kRolloutThreads, wave / kRolloutThreads * kRolloutThreads);
+  std::vector<long long> out;
   long long left = n_episodes;
-  for (long long c = C / 8; c < C && left > 2 * c; c *= 2) {
-    const long long cc = std::max<long long>(kRolloutThreads, c / kRolloutThreads * kRolloutThreads);
-    head.push_back(cc);
-    tail.push_back(cc);
-    left -= 2 * cc;
-  }
-  out = head;
+  const long long first_wave = std::min(left, wave);
+  long long head = std::max<long long>(kRolloutThreads, first_wave / 4 / kRolloutThreads * kRolloutThreads);
+  head = std::min(head, first_wave);
+  out.push_back(head);
+  if (first_wave > head) out.push_back(first_wave - head);
+  left -= first_wave;
   while (left > 0) {
-    const long long cc = std::min(C, left);
-    out.push_back(cc);
-    left -= cc;
+    long long c = std::min(wave, left);
+    if (left - c > 0 && left - c < wave / 8) c = left;      // no sliver at the end
+    out.push_back(c);
+    left -= c;
   }
-  out.insert(out.end(), tail.rbegin(), tail.rend());
   return out;
 }
 
@@ -1070,102 +1175,95 @@ int rollout_host_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, in
     set_error("bgr_rollout_host: h_params / h_init_state / h_metrics / h_status is NULL");
     return BGR_ERR_BAD_ARG;
   }
-  DeviceScope dev(track->device);
-  Scratch sc(stream);
-  const size_t E = static_cast<size_t>(n_episodes);
-  float* d_params;
-  double* d_init;
-  float* d_metrics;
-  int32_t* d_status;
-  double* d_traj = nullptr;
-  double* d_agg = nullptr;
-  double* d_partials = nullptr;
-  BGR_TRY(sc.get(&d_params, E * BGR_N_PARAMS));
-  BGR_TRY(sc.get(&d_init, E * BGR_N_STATE));
-  BGR_TRY(sc.get(&d_metrics, E * BGR_N_METRICS));
-  BGR_TRY(sc.get(&d_status, E * BGR_N_STATUS));
-  const size_t S = static_cast<size_t>(cfg->max_steps);
-  if (h_traj != nullptr) {
-    BGR_TRY(sc.get(&d_traj, E * S * BGR_N_TRAJ));
-    BGR_CUDA(cudaMemsetAsync(d_traj, 0, E * S * BGR_N_TRAJ * sizeof(double), stream));
-  }
-  if (E == 0) {
+  if (n_episodes == 0) {
     if (h_aggregate != nullptr) {
       const double zero[BGR_N_AGG] = {0, 0, 0, 0, 0, 1e300, 0, 0};
       std::memcpy(h_aggregate, zero, sizeof(zero));
     }
     return BGR_OK;
   }
-  const int grid_total = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
-  if (h_aggregate != nullptr) {
-    BGR_TRY(sc.get(&d_agg, BGR_N_AGG));
-    BGR_TRY(sc.get(&d_partials, static_cast<size_t>(grid_total) * BGR_N_AGG));
-  }
-  int32_t* d_work = nullptr;   // survivor lists of a two-phase run: one (count + 1)-sized slice per chunk
-  if (cfg->split_steps > 0 && static_cast<int>(cfg->split_steps) < cfg->max_steps)
-    BGR_TRY(sc.get(&d_work, E + static_cast<size_t>(n_episodes / kRolloutThreads) + 64));
+  DeviceScope dev(track->device);
   StepPlumbing sp;
   Plan plan;
   BGR_TRY(make_plan(track, cfg, sp, h_traj != nullptr, stream, &plan));
   BGR_TRY(ensure_pipeline(track->device));
   BGR_TRY(ensure_events(track->device));
+  const size_t E = static_cast<size_t>(n_episodes);
+  const size_t S = static_cast<size_t>(cfg->max_steps);
+  const bool two_phase = cfg->split_steps > 0 && static_cast<int>(cfg->split_steps) < cfg->max_steps;
+  const std::vector<long long> chunks = host_chunks(n_episodes, plan.wave);
+  const int grid_total = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
+  BGR_TRY(ensure_chunk_events(chunks.size()));
+  Slot* sl = nullptr;
+  BGR_TRY(acquire_slot(E, h_aggregate != nullptr ? static_cast<size_t>(grid_total) : 0,
+                       two_phase ? E + chunks.size() + 64 : 0, &sl));
+  // the trajectory dump (a debugging aid, synchronous calls only) is the one stream-ordered allocation left
+  Scratch sc(stream);
+  double* d_traj = nullptr;
+  if (h_traj != nullptr) {
+    BGR_TRY(sc.get(&d_traj, E * S * BGR_N_TRAJ));
+    BGR_CUDA(cudaMemsetAsync(d_traj, 0, E * S * BGR_N_TRAJ * sizeof(double), stream));
+  }
 
-  // If anything below fails half way, the internal streams may still be working on the scratch buffers that
-  // `sc` releases when this function returns: drain them first.
+  // If anything below fails half way, the internal streams may still be working on buffers the caller is about to
+  // reuse or free: drain them first.
   struct Drain {
     bool armed = true;
     ~Drain() {
-      if (armed) {
-        cudaStreamSynchronize(g_pipe.s[0]);
-        cudaStreamSynchronize(g_pipe.s[1]);
-      }
+      if (armed)
+        for (cudaStream_t st : {g_pipe.up, g_pipe.comp[0], g_pipe.comp[1], g_pipe.down}) cudaStreamSynchronize(st);
     }
   } drain;
-  // everything queued on the caller's stream so far (scratch allocation, memset) happens before the chunks
+  // everything queued on the caller's stream so far happens before the first upload
   BGR_CUDA(cudaEventRecord(g_pipe.ready, stream));
-  BGR_CUDA(cudaStreamWaitEvent(g_pipe.s[0], g_pipe.ready, 0));
-  BGR_CUDA(cudaStreamWaitEvent(g_pipe.s[1], g_pipe.ready, 0));
-  int c = 0;
+  BGR_CUDA(cudaStreamWaitEvent(g_pipe.up, g_pipe.ready, 0));
+  if (d_traj != nullptr)
+    for (int i = 0; i < 2; ++i) BGR_CUDA(cudaStreamWaitEvent(g_pipe.comp[i], g_pipe.ready, 0));
   long long e0 = 0;
-  for (const long long cnt : host_chunks(n_episodes)) {
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    const long long cnt = chunks[c];
     const size_t n = static_cast<size_t>(cnt), o = static_cast<size_t>(e0);
-    cudaStream_t st = g_pipe.s[c & 1];
-    BGR_CUDA(cudaMemcpyAsync(d_params + o * BGR_N_PARAMS, h_params + o * BGR_N_PARAMS, n * BGR_N_PARAMS * sizeof(float),
-                             cudaMemcpyHostToDevice, st));
-    BGR_CUDA(cudaMemcpyAsync(d_init + o * BGR_N_STATE, h_init_state + o * BGR_N_STATE, n * BGR_N_STATE * sizeof(double),
-                             cudaMemcpyHostToDevice, st));
-    const bool last = e0 + cnt >= n_episodes;
-    if (last) BGR_CUDA(cudaEventRecord(g_last.start, st));
-    BGR_TRY(launch_rollout_phases(plan, static_cast<int>(cfg->split_steps), e0, cnt, d_params + o * BGR_N_PARAMS,
-                                  d_init + o * BGR_N_STATE, d_metrics + o * BGR_N_METRICS, d_status + o * BGR_N_STATUS,
+    cudaEvent_t up_done = g_pipe.ev[2 * c], k_done = g_pipe.ev[2 * c + 1];
+    cudaStream_t cs = g_pipe.comp[c & 1];
+    BGR_CUDA(cudaMemcpyAsync(sl->d_params + o * BGR_N_PARAMS, h_params + o * BGR_N_PARAMS,
+                             n * BGR_N_PARAMS * sizeof(float), cudaMemcpyHostToDevice, g_pipe.up));
+    BGR_CUDA(cudaMemcpyAsync(sl->d_init + o * BGR_N_STATE, h_init_state + o * BGR_N_STATE,
+                             n * BGR_N_STATE * sizeof(double), cudaMemcpyHostToDevice, g_pipe.up));
+    BGR_CUDA(cudaEventRecord(up_done, g_pipe.up));
+    BGR_CUDA(cudaStreamWaitEvent(cs, up_done, 0));
+    const bool last = c + 1 == chunks.size();
+    if (last) BGR_CUDA(cudaEventRecord(g_last.start, cs));
+    BGR_TRY(launch_rollout_phases(plan, static_cast<int>(cfg->split_steps), e0, cnt, sl->d_params + o * BGR_N_PARAMS,
+                                  sl->d_init + o * BGR_N_STATE, sl->d_metrics + o * BGR_N_METRICS,
+                                  sl->d_status + o * BGR_N_STATUS,
                                   d_traj != nullptr ? d_traj + o * S * BGR_N_TRAJ : nullptr,
-                                  d_work != nullptr ? d_work + o + c : nullptr, st));
+                                  two_phase ? sl->d_work + o + c : nullptr, cs));
     if (last) {
-      BGR_CUDA(cudaEventRecord(g_last.stop, st));
+      BGR_CUDA(cudaEventRecord(g_last.stop, cs));
       g_last.valid = true;
     }
-    BGR_CUDA(cudaMemcpyAsync(h_metrics + o * BGR_N_METRICS, d_metrics + o * BGR_N_METRICS,
-                             n * BGR_N_METRICS * sizeof(float), cudaMemcpyDeviceToHost, st));
-    BGR_CUDA(cudaMemcpyAsync(h_status + o * BGR_N_STATUS, d_status + o * BGR_N_STATUS, n * BGR_N_STATUS * sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, st));
+    BGR_CUDA(cudaEventRecord(k_done, cs));
+    BGR_CUDA(cudaStreamWaitEvent(g_pipe.down, k_done, 0));
+    BGR_CUDA(cudaMemcpyAsync(h_metrics + o * BGR_N_METRICS, sl->d_metrics + o * BGR_N_METRICS,
+                             n * BGR_N_METRICS * sizeof(float), cudaMemcpyDeviceToHost, g_pipe.down));
+    BGR_CUDA(cudaMemcpyAsync(h_status + o * BGR_N_STATUS, sl->d_status + o * BGR_N_STATUS,
+                             n * BGR_N_STATUS * sizeof(int32_t), cudaMemcpyDeviceToHost, g_pipe.down));
     if (h_traj != nullptr)
       BGR_CUDA(cudaMemcpyAsync(h_traj + o * S * BGR_N_TRAJ, d_traj + o * S * BGR_N_TRAJ,
-                               n * S * BGR_N_TRAJ * sizeof(double), cudaMemcpyDeviceToHost, st));
+                               n * S * BGR_N_TRAJ * sizeof(double), cudaMemcpyDeviceToHost, g_pipe.down));
     e0 += cnt;
-    ++c;
   }
-  for (int i = 0; i < 2; ++i) {
-    BGR_CUDA(cudaEventRecord(g_pipe.done[i], g_pipe.s[i]));
-    BGR_CUDA(cudaStreamWaitEvent(stream, g_pipe.done[i], 0));
-  }
+  // the download stream has now waited for every chunk's kernel: the aggregate is computed from the complete rows
   if (h_aggregate != nullptr) {
-    BGR_CUDA(launch_aggregate_partials(d_metrics, d_status, n_episodes, d_partials, stream));
-    BGR_CUDA(launch_reduce_partials(d_partials, grid_total, d_agg, stream));
+    BGR_CUDA(launch_aggregate_partials(sl->d_metrics, sl->d_status, n_episodes, sl->d_partials, g_pipe.down));
+    BGR_CUDA(launch_reduce_partials(sl->d_partials, grid_total, sl->d_agg, g_pipe.down));
     count_launch(2);
-    BGR_CUDA(cudaMemcpyAsync(h_aggregate, d_agg, BGR_N_AGG * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    BGR_CUDA(cudaMemcpyAsync(h_aggregate, sl->d_agg, BGR_N_AGG * sizeof(double), cudaMemcpyDeviceToHost, g_pipe.down));
   }
-  // the caller's stream has waited on both internal streams: synchronising it completes the call; the scratch
-  // buffers are freed in stream order behind that wait either way
+  BGR_CUDA(cudaEventRecord(sl->done, g_pipe.down));
+  BGR_CUDA(cudaStreamWaitEvent(stream, sl->done, 0));
+  // the caller's stream has waited for the whole call: synchronising it completes it (and the trajectory scratch is
+  // freed in stream order behind that wait)
   if (synchronous) BGR_CUDA(cudaStreamSynchronize(stream));
   drain.armed = false;
   return BGR_OK;

@@ -53,6 +53,8 @@ struct TrackView {
   const float* guard2;
   const int2* rival_range;    // [n] (first, count) into rival_list; count < 0: none
   const int2* rival_list;     // (waypoint, bits of its squared reach-in distance), ascending per list
+  const int2* twin;           // [n] (twin waypoint t or -1, bits of the squared twin guard): inside it the exact argmin is
+                              // the best of the descent's answer and t - 1, t, t + 1 (bgr_api.cu: compute_guards)
   const int32_t* cone_range;  // [n] (first << 10) | count  into cone_list
   const float* cone_near;     // [n] distance from waypoint j to its closest listed cone, rounded down
   const int32_t* cone_list;

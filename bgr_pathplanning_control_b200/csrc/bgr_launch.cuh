@@ -6,11 +6,13 @@
 namespace bgr {
 
 template <typename Real, int STEER, int ACCEL, int MODEL, bool EXTRAS>
-cudaError_t launch_rollout(const RolloutArgs& args, int grid, size_t smem, int smem_optin, cudaStream_t stream);
+// `query_resident` != nullptr: no launch -- report how many episodes (threads) one SM holds at once with this kernel
+cudaError_t launch_rollout(const RolloutArgs& args, int grid, size_t smem, int smem_optin, cudaStream_t stream,
+                           int* query_resident);
 
 #define BGR_DECLARE_LAUNCH(Real, STEER, ACCEL, MODEL, EXTRAS) \
   template <>                                                \
-  cudaError_t launch_rollout<Real, STEER, ACCEL, MODEL, EXTRAS>(const RolloutArgs&, int, size_t, int, cudaStream_t);
+  cudaError_t launch_rollout<Real, STEER, ACCEL, MODEL, EXTRAS>(const RolloutArgs&, int, size_t, int, cudaStream_t, int*);
 
 #define BGR_FOR_ALL_LAWS(M, Real, EXTRAS) \
   M(Real, 0, 0, 0, EXTRAS)                \

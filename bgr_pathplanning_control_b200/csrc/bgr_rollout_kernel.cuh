@@ -639,11 +639,17 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const __grid_c
   template <>                                                                                            \
   cudaError_t launch_rollout<Real, STEER, ACCEL, MODEL, EXTRAS>(const RolloutArgs& args, int grid,        \
                                                                  size_t smem, int smem_optin,            \
-                                                                 cudaStream_t stream) {                  \
+                                                                 cudaStream_t stream, int* query_resident) { \
     auto kern = rollout_kernel<Real, STEER, ACCEL, MODEL, EXTRAS>;                                        \
     /* per-function attribute: always the device's opt-in maximum, so concurrent callers cannot lower it */ \
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin); \
     if (err != cudaSuccess) return err;                                                                  \
+    if (query_resident != nullptr) {                                                                     \
+      int ctas = 0;                                                                                      \
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kRolloutThreads, smem);           \
+      *query_resident = ctas * kRolloutThreads;                                                          \
+      return err;                                                                                        \
+    }                                                                                                    \
     kern<<<grid, kRolloutThreads, smem, stream>>>(args);                                                 \
     return cudaGetLastError();                                                                           \
   }

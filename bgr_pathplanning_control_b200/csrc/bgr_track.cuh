@@ -18,6 +18,7 @@ struct bgr_track {
   float* guard2 = nullptr;
   int2* rival_range = nullptr;     // per waypoint (first, count) into rival_list; count < 0: no usable list
   int2* rival_list = nullptr;      // (waypoint, float bits of the squared distance from w_j at which it can first win)
+  int2* twin = nullptr;            // per waypoint (twin waypoint t or -1, float bits of the squared twin guard)
   int32_t* cone_range = nullptr;
   float* cone_near = nullptr;   // [n] distance from waypoint j to its closest listed cone (rounded down)
   int32_t* cone_list = nullptr;
@@ -36,12 +37,12 @@ struct bgr_track {
   std::vector<double> x, y, kappa, path_yaw, guard_radius;
   double ds_min = 0, ds_max = 0, guard_min = 0, guard_median = 0;
   long long rival_total = 0;
-  int rival_max = 0, rival_unlisted = 0;
+  int rival_max = 0, rival_unlisted = 0, twin_count = 0;
 
   bgr::TrackView view() const {
     bgr::TrackView v;
     v.xy_f = xy_f; v.attr_f = attr_f; v.xy_d = xy_d; v.attr_d = attr_d; v.guard2 = guard2;
-    v.rival_range = rival_range; v.rival_list = rival_list;
+    v.rival_range = rival_range; v.rival_list = rival_list; v.twin = twin;
     v.cone_range = cone_range; v.cone_near = cone_near; v.cone_list = cone_list; v.cones = cones;
     v.n = n; v.n_pad = n_pad; v.closed = closed; v.n_cones = n_cones;
     v.ds_max = static_cast<float>(ds_max);

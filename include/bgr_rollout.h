@@ -12,9 +12,11 @@
  *     across the ABI; bgr_last_error_string() describes the last failure on the calling thread.
  *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensors); pointers named
  *     h_* are HOST pointers.  The library allocates nothing it does not free (stream ordered) before
- *     returning, except: the opaque track handle (with the LQG gain tables it caches on first use, freed
- *     by bgr_track_destroy) and, per calling host thread, two internal streams + a CUDA event pair used
- *     by the *_host entry points and bgr_last_kernel_ms.
+ *     returning, except: the opaque handles (track: with the LQG gain tables it caches on first use; MPC bank: with
+ *     the candidate statistics it caches per cost configuration) and, per calling host thread, the host-buffer
+ *     pipeline of bgr_rollout_host[_async] -- four internal streams, a pool of events and a ring of three device
+ *     buffer sets sized for the largest batch seen (released when the thread exits) -- plus the CUDA event pair of
+ *     bgr_last_kernel_ms.
  *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are asynchronous on
  *     that stream unless the name ends in _host (those synchronise the stream before returning).
  *   - handles are logically immutable after creation (the internal LQG table cache is mutex protected);
@@ -166,6 +168,8 @@ typedef struct bgr_track_info {
   int64_t rival_total;            /* total length of the rival lists of the nearest search */
   int32_t rival_max;              /* longest list */
   int32_t rival_unlisted;         /* waypoints without a usable list (exact scan outside their guard) */
+  int32_t twin_count;             /* waypoints with a twin triple (a second lap on the same line) */
+  int32_t reserved;
 } bgr_track_info_t;
 
 #define BGR_CFG_AUDIT 1 /* run the full kernel build so that the near-tie audit channel

@@ -485,6 +485,19 @@ def test_parity_stratified_over_the_whole_bench_sweep(oval, which):
     assert abs((res.metrics[:, abi.M_MAX_ABS_LAT] < OFF_TRACK_M).mean() - (m[:, 5] < OFF_TRACK_M).mean()) < 0.01
     fin = np.isfinite(res.metrics[:, abi.M_LAT_STD]) & np.isfinite(m[:, 1])
     assert abs(np.median(res.metrics[fin, abi.M_LAT_STD]) - np.median(m[fin, 1])) < 1e-3
+    # How wide does the tie band have to be?  The default 2e-5 m is ten times the worst-case fp32 evaluation error of a
+    # distance on this track (waypoint rounding 2.7e-6 m + arithmetic 5e-7 m).  The same batch audited with a 5e-6 m
+    # band: REPORTED, and it must still account for every on-track index mismatch.
+    narrow = bgr.rollout(track, bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=laps, audit=True,
+                                                  tie_eps=5e-6), params, init)
+    assert np.array_equal(narrow.metrics, res.metrics, equal_nan=True)
+    nflag = ~off_track & ~ill & (narrow.status[:, abi.S_NEAR_TIES] > 0)
+    unflagged_narrow = ~off_track & (narrow.status[:, abi.S_NEAR_TIES] == 0)
+    fr2 = {"tie_eps_m": 5e-6, "flagged": float(nflag.mean()), "good": float((~off_track & ~ill & ~nflag).mean()),
+           "unflagged_on_track_index_mismatches": int((mism & unflagged_narrow).sum()),
+           "good_max_dpos_m": float(dpos[~off_track & ~ill & ~nflag].max())}
+    _report_fractions(which + "_tie_band_5e-6", fr2)
+    assert fr2["unflagged_on_track_index_mismatches"] == 0, fr2
 
 
 def test_long_track_stages_only_the_xy_table(cuda_device):
