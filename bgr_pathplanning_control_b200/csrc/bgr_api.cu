@@ -1402,6 +1402,11 @@ struct bgr_mpc_bank {
   };
   std::mutex mu;
   std::vector<Stats> stats;
+  // device arena of the HOST entry point (states, outputs, evaluator scratch of one call), grown on demand: a call
+  // through the handle makes no allocation at all; host calls on one handle are serialised by `call_mu`
+  std::mutex call_mu;
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
 };
 
 namespace {
@@ -1411,7 +1416,7 @@ namespace {
 int mpc_eval_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes, const double* d_state,
                   const int32_t* d_ref_start, const int32_t* d_ref_len, const float* d_bank, int32_t n_candidates,
                   bgr_mpc_bank* bank_handle, float* d_best_u, float* d_best_cost, int32_t* d_best_idx, float* d_costs,
-                  cudaStream_t stream, const char* who) {
+                  cudaStream_t stream, const char* who, unsigned char* evaluator_scratch = nullptr) {
   BGR_TRY(validate_mpc(track, cfg, n_episodes, n_candidates, who));
   if (n_episodes == 0) return BGR_OK;
   if (d_state == nullptr || d_ref_start == nullptr || d_bank == nullptr) {
@@ -1471,8 +1476,8 @@ int mpc_eval_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_
   const size_t b_packed = (static_cast<size_t>(n_episodes) * sizeof(unsigned long long) + 255) & ~size_t(255);
   const size_t b_cand = (explicit_rollout || d_cand_cached != nullptr) ? 0 : (mpc_cand_bytes(n_candidates) + 255) & ~size_t(255);
   const size_t b_epi = explicit_rollout ? 0 : mpc_epi_bytes(n_episodes);
-  unsigned char* d_scratch;
-  BGR_TRY(sc.get(&d_scratch, b_packed + b_cand + b_epi));
+  unsigned char* d_scratch = evaluator_scratch;      // (sized by mpc_scratch_bytes; only with cached statistics)
+  if (d_scratch == nullptr || b_cand != 0) BGR_TRY(sc.get(&d_scratch, b_packed + b_cand + b_epi));
   unsigned long long* d_packed = reinterpret_cast<unsigned long long*>(d_scratch);
   if (explicit_rollout)
     BGR_CUDA(cudaMemsetAsync(d_packed, 0xff, static_cast<size_t>(n_episodes) * sizeof(unsigned long long), stream));
@@ -1522,23 +1527,52 @@ int mpc_eval_host_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64
   double* d_state;
   int32_t *d_start, *d_len = nullptr, *d_idx;
   float *d_bank = bank_handle != nullptr ? bank_handle->d_bank : nullptr, *d_u, *d_cost, *d_costs = nullptr;
-  BGR_TRY(sc.get(&d_state, E * 4));
-  BGR_TRY(sc.get(&d_start, E));
-  if (bank_handle == nullptr) BGR_TRY(sc.get(&d_bank, bank_count));
-  BGR_TRY(sc.get(&d_u, E * 2));
-  BGR_TRY(sc.get(&d_cost, E));
-  BGR_TRY(sc.get(&d_idx, E));
+  unsigned char* evaluator_scratch = nullptr;
+  std::unique_lock<std::mutex> call_lock;
+  if (bank_handle != nullptr) {
+    // everything but the optional cost matrix comes out of the handle's arena: [state | start | len | u | cost | idx |
+    // evaluator scratch], 256-byte aligned pieces
+    call_lock = std::unique_lock<std::mutex>(bank_handle->call_mu);
+    auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t o_state = 0, o_start = o_state + up(E * 4 * sizeof(double)), o_len = o_start + up(E * sizeof(int32_t)),
+                 o_u = o_len + up(E * sizeof(int32_t)), o_cost = o_u + up(E * 2 * sizeof(float)),
+                 o_idx = o_cost + up(E * sizeof(float)), o_eval = o_idx + up(E * sizeof(int32_t)),
+                 total = o_eval + up(E * sizeof(unsigned long long)) + up(mpc_epi_bytes(n_episodes)) + 256;
+    if (bank_handle->arena_bytes < total) {
+      BGR_CUDA(cudaStreamSynchronize(stream));
+      cudaFree(bank_handle->arena);
+      bank_handle->arena = nullptr;
+      bank_handle->arena_bytes = 0;
+      BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&bank_handle->arena), total + total / 4));
+      bank_handle->arena_bytes = total + total / 4;
+    }
+    unsigned char* a = bank_handle->arena;
+    d_state = reinterpret_cast<double*>(a + o_state);
+    d_start = reinterpret_cast<int32_t*>(a + o_start);
+    if (h_ref_len != nullptr) d_len = reinterpret_cast<int32_t*>(a + o_len);
+    d_u = reinterpret_cast<float*>(a + o_u);
+    d_cost = reinterpret_cast<float*>(a + o_cost);
+    d_idx = reinterpret_cast<int32_t*>(a + o_idx);
+    evaluator_scratch = a + o_eval;
+  } else {
+    BGR_TRY(sc.get(&d_state, E * 4));
+    BGR_TRY(sc.get(&d_start, E));
+    BGR_TRY(sc.get(&d_bank, bank_count));
+    BGR_TRY(sc.get(&d_u, E * 2));
+    BGR_TRY(sc.get(&d_cost, E));
+    BGR_TRY(sc.get(&d_idx, E));
+  }
   BGR_CUDA(cudaMemcpyAsync(d_state, h_state, E * 4 * sizeof(double), cudaMemcpyHostToDevice, stream));
   BGR_CUDA(cudaMemcpyAsync(d_start, h_ref_start, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   if (bank_handle == nullptr)
     BGR_CUDA(cudaMemcpyAsync(d_bank, h_bank, bank_count * sizeof(float), cudaMemcpyHostToDevice, stream));
   if (h_ref_len != nullptr) {
-    BGR_TRY(sc.get(&d_len, E));
+    if (d_len == nullptr) BGR_TRY(sc.get(&d_len, E));
     BGR_CUDA(cudaMemcpyAsync(d_len, h_ref_len, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   }
   if (h_costs != nullptr) BGR_TRY(sc.get(&d_costs, E * K));
   BGR_TRY(mpc_eval_core(track, cfg, n_episodes, d_state, d_start, d_len, d_bank, n_candidates, bank_handle, d_u, d_cost,
-                        d_idx, d_costs, stream, who));
+                        d_idx, d_costs, stream, who, evaluator_scratch));
   if (h_best_u != nullptr)
     BGR_CUDA(cudaMemcpyAsync(h_best_u, d_u, E * 2 * sizeof(float), cudaMemcpyDeviceToHost, stream));
   if (h_best_cost != nullptr)
@@ -1625,6 +1659,7 @@ extern "C" void bgr_mpc_bank_destroy(bgr_mpc_bank_t* bank) {
   if (bank == nullptr) return;
   DeviceScope dev(bank->device);
   cudaFree(bank->d_bank);
+  cudaFree(bank->arena);
   for (auto& st : bank->stats) cudaFree(st.d_cand);
   delete bank;
 }

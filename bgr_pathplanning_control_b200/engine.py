@@ -599,14 +599,14 @@ def fp64_peak_probe(device=0):
     return t.value
 
 
-def mpc_evaluate(track, config, state, ref_start, bank, ref_len=None, *, return_costs=False, time_kernel=False):
+def mpc_evaluate(track, config, state, ref_start, bank, ref_len=None, *, return_costs=False, time_kernel=False, out=None):
     """Score every candidate control sequence of ``bank`` (K, H, 2) -- an array, or a resident ``MpcBank`` -- for every
     episode state (E, 4) = ``[x, y, yaw, v]`` and pick the cheapest feasible one.  CUDA tensors (zero copy, async) or
     numpy arrays (host entry point)."""
     lib = abi.load()
     cfg = config.to_struct() if isinstance(config, MpcConfig) else config
     if isinstance(bank, MpcBank):
-        return _mpc_evaluate_bank(lib, track, cfg, state, ref_start, bank, ref_len, return_costs, time_kernel)
+        return _mpc_evaluate_bank(lib, track, cfg, state, ref_start, bank, ref_len, return_costs, time_kernel, out)
     if isinstance(state, np.ndarray):
         state = _np(state, np.float64)
         E = state.shape[0]
@@ -642,7 +642,9 @@ def mpc_evaluate(track, config, state, ref_start, bank, ref_len=None, *, return_
     return MpcResult(u, cost, idx, costs, ms)
 
 
-def _mpc_evaluate_bank(lib, track, cfg, state, ref_start, bank, ref_len, return_costs, time_kernel):
+def _mpc_evaluate_bank(lib, track, cfg, state, ref_start, bank, ref_len, return_costs, time_kernel, out=None):
+    """``out``: an ``MpcResult`` of (E, 2) float32 / (E,) float32 / (E,) int32 host arrays to fill (pinned buffers make
+    the copies asynchronous; a streaming caller reuses one result object per control period)."""
     K = bank.K
     if isinstance(state, np.ndarray):
         state = _np(state, np.float64)
@@ -650,9 +652,15 @@ def _mpc_evaluate_bank(lib, track, cfg, state, ref_start, bank, ref_len, return_
         state = _np(state, np.float64, (E, 4))
         ref_start = _np(ref_start, np.int32, (E,))
         ref_len = None if ref_len is None else _np(ref_len, np.int32, (E,))
-        u = np.empty((E, 2), np.float32)
-        cost = np.empty(E, np.float32)
-        idx = np.empty(E, np.int32)
+        if out is not None:
+            u, cost, idx = out.best_u, out.best_cost, out.best_idx
+            if (u.dtype != np.float32 or u.shape != (E, 2) or cost.dtype != np.float32 or cost.shape != (E,)
+                    or idx.dtype != np.int32 or idx.shape != (E,)):
+                raise ValueError("out must hold (E, 2) float32, (E,) float32 and (E,) int32 arrays")
+        else:
+            u = np.empty((E, 2), np.float32)
+            cost = np.empty(E, np.float32)
+            idx = np.empty(E, np.int32)
         costs = np.empty((E, K), np.float32) if return_costs else None
         abi.check(lib.bgr_mpc_eval_bank_host(track.handle, C.byref(cfg), E, _ptr(state), _ptr(ref_start), _ptr(ref_len),
                                              bank.handle, _ptr(u), _ptr(cost), _ptr(idx), _ptr(costs), None))
