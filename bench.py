@@ -581,7 +581,7 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
         lo = (rank * len(kinds) + g) * per
         split = max(0, int(os.environ.get("BGR_MC_SPLIT", "0")))
         cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=1, episode_id_base=lo,
-                                split_steps=split, **noise)
+                                split_steps=split, static_schedule=os.environ.get("BGR_MC_STATIC") == "1", **noise)
         init = bgr.initial_states(ta, per, index=0, v0=5.0 if model == "dynamic" else 0.0)
         init[:, abi.YAW] = 0.0
         params = bgr.sweeps.monte_carlo_params(per, start=lo)
@@ -670,6 +670,8 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
                    "cone_hits_last_step_rank0": hits, "parallelism": f"episode sharding x{world}",
                    "launch": "kinds back to back on one stream" if serial else
                              "kinds on three concurrent streams, latency-bound Stanley kinds first",
+                   "schedule": "static (one episode per thread)" if os.environ.get("BGR_MC_STATIC") == "1" else
+                               "dynamic (one-wave grids; lanes pull their next episode from a queue)",
                    "l2": "state lives in registers; 112 B in + 88 B out per episode"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per * len(kinds) * 112,

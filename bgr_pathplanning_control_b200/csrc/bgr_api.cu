@@ -689,6 +689,9 @@ struct Plan {
   size_t smem = 0;
   int smem_optin = 0;   // the device's opt-in shared-memory maximum (per-function attribute of every step kernel)
   long long wave = 0;   // episodes the device runs at once with this kernel (SMs x resident CTAs x threads)
+  // dynamic episode scheduling (full fp32 build, plain rollouts): one wave of CTAs pulls rows from a device counter
+  bool dynamic = false;
+  long long wave_dyn = 0;
 };
 
 // Validate the configuration, fill the kernel arguments that do not depend on the episode range, pick the kernel
@@ -841,6 +844,17 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   int resident = 0;
   BGR_CUDA(plan->fn(A, 0, plan->smem, plan->smem_optin, nullptr, &resident));
   plan->wave = static_cast<long long>(di.sm_count) * std::max(resident, kRolloutThreads);
+  // Dynamic scheduling pays when episodes end at very different times; it is offered for every plain rollout of the
+  // full fp32 build (the single-step plumbing and the explicit two-phase request keep the static schedule) and used by
+  // the launch sites for batches larger than one wave.  BGR_CFG_STATIC_SCHEDULE switches it off.
+  plan->dynamic = full && !f64 && sp.ctrl_in == nullptr && !sp.force_full && cfg->split_steps == 0 &&
+                  !(cfg->flags & BGR_CFG_STATIC_SCHEDULE);
+  if (plan->dynamic) {
+    RolloutArgs Q = A;
+    Q.queue = reinterpret_cast<int32_t*>(uintptr_t(16));   // (only selects the instantiation: nothing is launched)
+    BGR_CUDA(plan->fn(Q, 0, plan->smem, plan->smem_optin, nullptr, &resident));
+    plan->wave_dyn = static_cast<long long>(di.sm_count) * std::max(resident, kRolloutThreads);
+  }
   return BGR_OK;
 }
 
@@ -850,7 +864,7 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
 // work on row d_idx[t] for t < *d_count (second phase).
 int launch_range(const Plan& plan, long long id_offset, long long count, const float* d_params, const double* d_init,
                  float* d_metrics, int32_t* d_status, double* d_traj, int max_steps, const int32_t* d_idx,
-                 const int32_t* d_count, cudaStream_t stream) {
+                 const int32_t* d_count, cudaStream_t stream, int32_t* d_queue = nullptr) {
   RolloutArgs A = plan.A;
   A.params = d_params;
   A.init = d_init;
@@ -863,7 +877,13 @@ int launch_range(const Plan& plan, long long id_offset, long long count, const f
   A.max_steps = max_steps;
   A.idx = d_idx;
   A.count = d_count;
-  const int grid = static_cast<int>((count + kRolloutThreads - 1) / kRolloutThreads);
+  int grid = static_cast<int>((count + kRolloutThreads - 1) / kRolloutThreads);
+  if (d_queue != nullptr && plan.dynamic && d_idx == nullptr && count > plan.wave_dyn) {
+    // dynamic schedule: one wave of CTAs, rows pulled from a zeroed counter
+    BGR_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int32_t), stream));
+    A.queue = d_queue;
+    grid = static_cast<int>(std::min<long long>(grid, plan.wave_dyn / kRolloutThreads));
+  }
   cudaError_t err = plan.fn(A, grid, plan.smem, plan.smem_optin, stream, nullptr);
   if (err == cudaSuccess) count_launch();
   return check_cuda(err, "rollout kernel launch");
@@ -877,10 +897,11 @@ int launch_range(const Plan& plan, long long id_offset, long long count, const f
 // `d_work` is scratch for the survivor list: int32[count + 1] (last element = number of survivors).
 int launch_rollout_phases(const Plan& plan, int split_steps, long long id_offset, long long count, const float* d_params,
                           const double* d_init, float* d_metrics, int32_t* d_status, double* d_traj, int32_t* d_work,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int32_t* d_queue = nullptr) {
   const int S = plan.A.max_steps;
   if (split_steps <= 0 || split_steps >= S || d_work == nullptr)
-    return launch_range(plan, id_offset, count, d_params, d_init, d_metrics, d_status, d_traj, S, nullptr, nullptr, stream);
+    return launch_range(plan, id_offset, count, d_params, d_init, d_metrics, d_status, d_traj, S, nullptr, nullptr, stream,
+                        d_queue);
   int rc = launch_range(plan, id_offset, count, d_params, d_init, d_metrics, d_status, d_traj, split_steps, nullptr,
                         nullptr, stream);
   if (rc != BGR_OK) return rc;
@@ -951,10 +972,14 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   if (split > 0 && split < cfg->max_steps)
     BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_work), static_cast<size_t>(n_episodes + 1) * sizeof(int32_t),
                              stream));
+  int32_t* d_queue = nullptr;
+  if (plan.dynamic && n_episodes > plan.wave_dyn)
+    BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_queue), sizeof(int32_t), stream));
   rc = ensure_events(track->device);
   if (rc == BGR_OK) rc = check_cuda(cudaEventRecord(g_last.start, stream), "cudaEventRecord");
   if (rc == BGR_OK)
-    rc = launch_rollout_phases(plan, split, 0, n_episodes, d_params, d_init, d_metrics, d_status, d_traj, d_work, stream);
+    rc = launch_rollout_phases(plan, split, 0, n_episodes, d_params, d_init, d_metrics, d_status, d_traj, d_work, stream,
+                               d_queue);
   if (rc == BGR_OK) {
     rc = check_cuda(cudaEventRecord(g_last.stop, stream), "cudaEventRecord");
     g_last.valid = rc == BGR_OK;
@@ -966,6 +991,7 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   }
   if (d_partials != nullptr) cudaFreeAsync(d_partials, stream);
   if (d_work != nullptr) cudaFreeAsync(d_work, stream);
+  if (d_queue != nullptr) cudaFreeAsync(d_queue, stream);
   return rc;
 }
 
@@ -1043,9 +1069,11 @@ struct Slot {
   double* d_partials = nullptr;
   double* d_agg = nullptr;
   int32_t* d_work = nullptr;
+  int32_t* d_queue = nullptr;   // [kMaxQueueChunks] row counters of dynamically scheduled chunk launches
   cudaEvent_t done = nullptr;
   bool used = false;
 };
+constexpr int kMaxQueueChunks = 256;
 struct Pipeline {
   int device = -1;
   cudaStream_t up = nullptr, down = nullptr, comp[2] = {nullptr, nullptr};
@@ -1069,7 +1097,7 @@ struct Pipeline {
     ev.clear();
     for (Slot& sl : slot) {
       cudaFree(sl.d_params); cudaFree(sl.d_init); cudaFree(sl.d_metrics); cudaFree(sl.d_status);
-      cudaFree(sl.d_partials); cudaFree(sl.d_agg); cudaFree(sl.d_work);
+      cudaFree(sl.d_partials); cudaFree(sl.d_agg); cudaFree(sl.d_work); cudaFree(sl.d_queue);
       if (sl.done != nullptr) cudaEventDestroy(sl.done);
       sl = Slot();
     }
@@ -1127,6 +1155,7 @@ int acquire_slot(size_t E, size_t n_partials, size_t n_work, Slot** out) {
     sl.cap_partials = n_partials + n_partials / 8 + 8;
   }
   if (sl.d_agg == nullptr) BGR_TRY(grow(&sl.d_agg, BGR_N_AGG));
+  if (sl.d_queue == nullptr) BGR_TRY(grow(&sl.d_queue, kMaxQueueChunks));
   if (sl.cap_work < n_work) {
     BGR_TRY(grow(&sl.d_work, n_work + n_work / 8 + 64));
     sl.cap_work = n_work + n_work / 8 + 64;
@@ -1191,7 +1220,9 @@ int rollout_host_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, in
   const size_t E = static_cast<size_t>(n_episodes);
   const size_t S = static_cast<size_t>(cfg->max_steps);
   const bool two_phase = cfg->split_steps > 0 && static_cast<int>(cfg->split_steps) < cfg->max_steps;
-  const std::vector<long long> chunks = host_chunks(n_episodes, plan.wave);
+  // a dynamically scheduled kernel wants MANY episodes per launch (its lanes refill from the queue): four waves per
+  // chunk instead of one
+  const std::vector<long long> chunks = host_chunks(n_episodes, plan.dynamic ? 4 * plan.wave_dyn : plan.wave);
   const int grid_total = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
   BGR_TRY(ensure_chunk_events(chunks.size()));
   Slot* sl = nullptr;
@@ -1237,7 +1268,8 @@ int rollout_host_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, in
                                   sl->d_init + o * BGR_N_STATE, sl->d_metrics + o * BGR_N_METRICS,
                                   sl->d_status + o * BGR_N_STATUS,
                                   d_traj != nullptr ? d_traj + o * S * BGR_N_TRAJ : nullptr,
-                                  two_phase ? sl->d_work + o + c : nullptr, cs));
+                                  two_phase ? sl->d_work + o + c : nullptr, cs,
+                                  c < static_cast<size_t>(kMaxQueueChunks) ? sl->d_queue + c : nullptr));
     if (last) {
       BGR_CUDA(cudaEventRecord(g_last.stop, cs));
       g_last.valid = true;

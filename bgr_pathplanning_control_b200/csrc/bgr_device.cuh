@@ -89,6 +89,8 @@ struct RolloutArgs {
   const float2* kf_gain_f; // the same sequence rounded to fp32 (production kernels)
   int32_t kf_len;
   // two-phase execution (episodes that outlive the first, short launch are re-run from scratch, densely packed):
+  int32_t* queue;         // nullptr (static schedule), or a zeroed device counter: DYNAMIC episode scheduling -- every
+                          // lane of a one-wave grid pulls its next row from it (full fp32 build only)
   const int32_t* idx;     // nullptr, or [count] episode row handled by thread t (rows of params / init / outputs)
   const int32_t* count;   // nullptr (= n_episodes threads are live), or device scalar: number of live threads
   long long n_episodes;

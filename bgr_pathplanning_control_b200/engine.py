@@ -115,6 +115,7 @@ class RolloutConfig:
     laps: int = 1                    # PP: base lap tiled this many times (monotone target index)
     laps_target: int = 0
     audit: bool = False              # fill the near-tie audit channel (full kernel build)
+    static_schedule: bool = False    # one episode per thread even where episodes would be scheduled dynamically
     dt: float = conf.dt
     wheelbase: float = conf.WB
     l_f: float = conf.l_f
@@ -151,7 +152,8 @@ class RolloutConfig:
         except KeyError as e:
             raise ValueError(f"Unknown controller / model / precision: {e.args[0]}") from None
         c.max_steps, c.laps, c.laps_target = int(self.max_steps), int(self.laps), int(self.laps_target)
-        c.flags = (abi.CFG_AUDIT if self.audit else 0) | (abi.CFG_STANLEY_SHADOWED if self.stanley_shadowed else 0)
+        c.flags = ((abi.CFG_AUDIT if self.audit else 0) | (abi.CFG_STANLEY_SHADOWED if self.stanley_shadowed else 0)
+                   | (abi.CFG_STATIC_SCHEDULE if self.static_schedule else 0))
         c.stanley_max_steer_rate, c.stanley_alpha = float(self.stanley_max_steer_rate), float(self.stanley_alpha)
         c.stanley_lookahead = float(self.stanley_lookahead)
         for k in ("dt", "wheelbase", "l_f", "l_r", "max_steer", "max_accel", "max_decel", "hit_radius", "tie_eps",

@@ -178,6 +178,11 @@ typedef struct bgr_track_info {
                            core/controllers.py:234-324 -- adaptive gain k / (v + k_soft), steering-rate limit, low-pass
                            filter, carried previous_steering.  A labelled extra: the live law is :336-385. */
 
+#define BGR_CFG_STATIC_SCHEDULE 4 /* keep one episode per thread even where the library would schedule episodes
+                           dynamically (full-build rollouts of more than one wave of episodes: every lane of a one-wave
+                           grid pulls its next row from a queue when its episode ends).  Results are bit-identical either
+                           way; the flag exists for measurements and tests. */
+
 typedef struct bgr_rollout_cfg {
   int32_t steer_kind, accel_kind, model_kind, precision;
   int32_t max_steps;       /* step cap (legacy loop: T / dt, old/animation_loop.py:16-17,71) */

@@ -677,3 +677,36 @@ def test_async_host_rollouts_pipeline_and_equal_the_synchronous_call(oval, cuda_
         assert np.array_equal(g.aggregate, ref.aggregate) and g.aggregate[abi.A_EPISODES] == E
         assert pend[0].wait() is got[0]          # wait() is idempotent
 
+
+@pytest.mark.parametrize("steer,accel,model", [("pure_pursuit", "pid", "kinematic"), ("stanley", "pid", "kinematic"),
+                                               ("stanley", "lqg", "dynamic")])
+def test_dynamic_episode_scheduling_is_bit_identical(cuda_device, steer, accel, model):
+    """Full-build rollouts of more than one wave of episodes are scheduled DYNAMICALLY: a one-wave grid whose lanes pull
+    their next row from a queue when their episode ends (Monte Carlo episodes end anywhere between 100 and 1 500
+    steps).  Every row must equal the static one-episode-per-thread schedule bit for bit -- device tensors and host
+    buffers -- and the batch must actually be large enough to take the dynamic path."""
+    import torch
+    ta = bgr.tracks.skidpad(2048)
+    track = bgr.Track.from_arrays(ta, cone_reach=4.0)
+    E = 148 * 2 * 256 + 40001                      # more than one wave of the 2-CTA full build, and ragged
+    noise = dict(sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1, sigma_cone=0.05, noise_seed=7, hit_radius=0.5,
+                 episode_id_base=12345)
+    params = bgr.sweeps.monte_carlo_params(E, start=777)
+    init = bgr.initial_states(ta, E, index=0, v0=5.0 if model == "dynamic" else 0.0)
+    init[:, abi.YAW] = 0.0
+    dp, di = torch.from_numpy(params).to(cuda_device), torch.from_numpy(init).to(cuda_device)
+    out = {}
+    for static in (True, False):
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=1, static_schedule=static,
+                                **noise)
+        r = bgr.rollout(track, cfg, dp, di, aggregate=True)
+        out[static] = (r.metrics.cpu().numpy(), r.status.cpu().numpy(), r.aggregate.cpu().numpy())
+        if not static:
+            host = bgr.rollout(track, cfg, params, init, aggregate=True)
+            assert np.array_equal(host.metrics, out[static][0], equal_nan=True) and np.array_equal(host.status, out[static][1])
+    assert np.array_equal(out[True][0], out[False][0], equal_nan=True)
+    assert np.array_equal(out[True][1], out[False][1])
+    assert np.array_equal(out[True][2], out[False][2])
+    steps = out[True][1][:, abi.S_STEPS]
+    assert steps.min() >= 1 and steps.max() > 3 * steps.mean() or steer == "pure_pursuit"    # heavy-tailed lengths
+
