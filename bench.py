@@ -581,14 +581,15 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
         lo = (rank * len(kinds) + g) * per
         split = max(0, int(os.environ.get("BGR_MC_SPLIT", "0")))
         cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=1, episode_id_base=lo,
-                                split_steps=split, static_schedule=os.environ.get("BGR_MC_STATIC") == "1", **noise)
+                                split_steps=split, dynamic_schedule=os.environ.get("BGR_MC_DYNAMIC") == "1", **noise)
         init = bgr.initial_states(ta, per, index=0, v0=5.0 if model == "dynamic" else 0.0)
         init[:, abi.YAW] = 0.0
         params = bgr.sweeps.monte_carlo_params(per, start=lo)
         out = bgr.RolloutResult(torch.empty((per, abi.N_METRICS), dtype=torch.float32, device=dev),
                                 torch.empty((per, abi.N_STATUS), dtype=torch.int32, device=dev), None,
                                 torch.empty(abi.N_AGG, dtype=torch.float64, device=dev))
-        jobs.append((cfg, torch.from_numpy(params).to(dev), torch.from_numpy(init).to(dev), out, params, init))
+        jobs.append((cfg, torch.from_numpy(params).to(dev), torch.from_numpy(init).to(dev), out,
+                     torch.from_numpy(params).pin_memory().numpy(), torch.from_numpy(init).pin_memory().numpy()))
 
     # the three kinds run on concurrent streams, the latency-bound Stanley kinds first (engine.rollout_groups);
     # BGR_MC_SERIAL=1 launches them back to back on one stream instead
@@ -641,7 +642,9 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
             assert m_all.shape[0] == n_all and torch.equal(s_all[: s.shape[0]], s)
             assert int(s_all[:, abi.S_STEPS].to(torch.int64).sum().item()) == int(round(total_steps / steps))
         del m_all, s_all
-    # e2e: host buffers (one host thread per kind through bgr_rollout_host)
+    # e2e: host buffers (one persistent host thread per kind through bgr_rollout_host)
+    for _ in range(2):      # (the worker threads build their copy / compute pipelines on first use)
+        bgr.rollout_groups(track, [(j[0], j[4], j[5]) for j in jobs], aggregate=True, order=[2, 1, 0])
     w0 = time.perf_counter()
     e2e_steps = 0.0
     for _ in range(steps):
@@ -670,8 +673,8 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
                    "cone_hits_last_step_rank0": hits, "parallelism": f"episode sharding x{world}",
                    "launch": "kinds back to back on one stream" if serial else
                              "kinds on three concurrent streams, latency-bound Stanley kinds first",
-                   "schedule": "static (one episode per thread)" if os.environ.get("BGR_MC_STATIC") == "1" else
-                               "dynamic (one-wave grids; lanes pull their next episode from a queue)",
+                   "schedule": "dynamic (one-wave grids; lanes pull their next episode from a queue)"
+                               if os.environ.get("BGR_MC_DYNAMIC") == "1" else "static (one episode per thread)",
                    "l2": "state lives in registers; 112 B in + 88 B out per episode"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per * len(kinds) * 112,

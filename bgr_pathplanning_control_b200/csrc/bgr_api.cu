@@ -844,11 +844,13 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   int resident = 0;
   BGR_CUDA(plan->fn(A, 0, plan->smem, plan->smem_optin, nullptr, &resident));
   plan->wave = static_cast<long long>(di.sm_count) * std::max(resident, kRolloutThreads);
-  // Dynamic scheduling pays when episodes end at very different times; it is offered for every plain rollout of the
-  // full fp32 build (the single-step plumbing and the explicit two-phase request keep the static schedule) and used by
-  // the launch sites for batches larger than one wave.  BGR_CFG_STATIC_SCHEDULE switches it off.
-  plan->dynamic = full && !f64 && sp.ctrl_in == nullptr && !sp.force_full && cfg->split_steps == 0 &&
-                  !(cfg->flags & BGR_CFG_STATIC_SCHEDULE);
+  // Dynamic scheduling (BGR_CFG_DYNAMIC_SCHEDULE) is for batches whose episodes end at very different times AND whose
+  // longest episodes are rare enough for the refilled lanes to matter; plain rollouts of the full fp32 build only (the
+  // single-step plumbing and an explicit two-phase request keep the static schedule), used by the launch sites for
+  // batches larger than one wave.  Measured on config 5: neutral -- that workload is bound by its
+  // per-step cost, not by stragglers -- so it is opt-in.
+  plan->dynamic = (cfg->flags & BGR_CFG_DYNAMIC_SCHEDULE) != 0 && full && !f64 && sp.ctrl_in == nullptr &&
+                  !sp.force_full && cfg->split_steps == 0;
   if (plan->dynamic) {
     RolloutArgs Q = A;
     Q.queue = reinterpret_cast<int32_t*>(uintptr_t(16));   // (only selects the instantiation: nothing is launched)

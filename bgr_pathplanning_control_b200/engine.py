@@ -115,7 +115,7 @@ class RolloutConfig:
     laps: int = 1                    # PP: base lap tiled this many times (monotone target index)
     laps_target: int = 0
     audit: bool = False              # fill the near-tie audit channel (full kernel build)
-    static_schedule: bool = False    # one episode per thread even where episodes would be scheduled dynamically
+    dynamic_schedule: bool = False   # full build, > 1 wave of episodes: lanes pull their next episode from a queue
     dt: float = conf.dt
     wheelbase: float = conf.WB
     l_f: float = conf.l_f
@@ -153,7 +153,7 @@ class RolloutConfig:
             raise ValueError(f"Unknown controller / model / precision: {e.args[0]}") from None
         c.max_steps, c.laps, c.laps_target = int(self.max_steps), int(self.laps), int(self.laps_target)
         c.flags = ((abi.CFG_AUDIT if self.audit else 0) | (abi.CFG_STANLEY_SHADOWED if self.stanley_shadowed else 0)
-                   | (abi.CFG_STATIC_SCHEDULE if self.static_schedule else 0))
+                   | (abi.CFG_DYNAMIC_SCHEDULE if self.dynamic_schedule else 0))
         c.stanley_max_steer_rate, c.stanley_alpha = float(self.stanley_max_steer_rate), float(self.stanley_alpha)
         c.stanley_lookahead = float(self.stanley_lookahead)
         for k in ("dt", "wheelbase", "l_f", "l_r", "max_steer", "max_accel", "max_decel", "hit_radius", "tie_eps",
@@ -292,6 +292,17 @@ def rollout(track, config, params, init_state, *, traj=False, aggregate=False, o
 
 
 _group_streams = {}
+_group_pool = None
+
+
+def _host_group_pool(n):
+    global _group_pool
+    if _group_pool is None or _group_pool._max_workers < n:
+        from concurrent.futures import ThreadPoolExecutor
+        if _group_pool is not None:
+            _group_pool.shutdown(wait=True)
+        _group_pool = ThreadPoolExecutor(max_workers=max(n, 4), thread_name_prefix="bgr-group")
+    return _group_pool
 
 
 def rollout_groups(track, groups, *, aggregate=False, outs=None, order=None):
@@ -304,11 +315,12 @@ def rollout_groups(track, groups, *, aggregate=False, outs=None, order=None):
     ``bgr_rollout_host`` (ctypes drops the GIL; the library's copy / compute pipeline is per thread), synchronous."""
     seq = list(order) if order is not None else list(range(len(groups)))
     if any(isinstance(g[1], np.ndarray) or isinstance(g[2], np.ndarray) for g in groups):
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=len(groups)) as pool:
-            futs = {g: pool.submit(rollout, track, groups[g][0], groups[g][1], groups[g][2], aggregate=aggregate,
-                                   out=None if outs is None else outs[g]) for g in seq}
-            return [futs[g].result() for g in range(len(groups))]
+        # worker threads PERSIST across calls: the library keeps its host-buffer pipeline (streams, device buffer ring)
+        # per host thread, and a fresh thread would have to build it again
+        pool = _host_group_pool(len(groups))
+        futs = {g: pool.submit(rollout, track, groups[g][0], groups[g][1], groups[g][2], aggregate=aggregate,
+                               out=None if outs is None else outs[g]) for g in seq}
+        return [futs[g].result() for g in range(len(groups))]
     torch = _torch()
     dev = torch.device("cuda", track.device)
     main = torch.cuda.current_stream(dev)

@@ -178,10 +178,10 @@ typedef struct bgr_track_info {
                            core/controllers.py:234-324 -- adaptive gain k / (v + k_soft), steering-rate limit, low-pass
                            filter, carried previous_steering.  A labelled extra: the live law is :336-385. */
 
-#define BGR_CFG_STATIC_SCHEDULE 4 /* keep one episode per thread even where the library would schedule episodes
-                           dynamically (full-build rollouts of more than one wave of episodes: every lane of a one-wave
-                           grid pulls its next row from a queue when its episode ends).  Results are bit-identical either
-                           way; the flag exists for measurements and tests. */
+#define BGR_CFG_DYNAMIC_SCHEDULE 4 /* full-build rollouts of more than one wave of episodes: a one-wave grid whose lanes
+                           pull their next row from a queue the moment their episode ends, instead of one episode per
+                           thread.  For batches with heavy-tailed episode lengths; output rows are bit-identical either
+                           way.  Off by default (measured neutral on BASELINE config 5). */
 
 typedef struct bgr_rollout_cfg {
   int32_t steer_kind, accel_kind, model_kind, precision;

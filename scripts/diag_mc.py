@@ -21,7 +21,8 @@ kinds = [("pure_pursuit", "pid", "kinematic"), ("stanley", "pid", "kinematic"), 
 for g, (steer, accel, model) in enumerate(kinds):
     for label, extra in (("noise+cones", noise), ("noise only", {**noise, "hit_radius": 0.0}),
                          ("clean (lean build)", {})):
-        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=1, episode_id_base=g * per, **extra)
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=1, episode_id_base=g * per,
+                                dynamic_schedule=os.environ.get("BGR_MC_DYNAMIC") == "1", **extra)
         init = bgr.initial_states(ta, per, index=0, v0=5.0 if model == "dynamic" else 0.0)
         init[:, abi.YAW] = 0.0
         p = torch.from_numpy(bgr.sweeps.monte_carlo_params(per, start=g * per)).to(dev)

@@ -681,10 +681,10 @@ def test_async_host_rollouts_pipeline_and_equal_the_synchronous_call(oval, cuda_
 @pytest.mark.parametrize("steer,accel,model", [("pure_pursuit", "pid", "kinematic"), ("stanley", "pid", "kinematic"),
                                                ("stanley", "lqg", "dynamic")])
 def test_dynamic_episode_scheduling_is_bit_identical(cuda_device, steer, accel, model):
-    """Full-build rollouts of more than one wave of episodes are scheduled DYNAMICALLY: a one-wave grid whose lanes pull
-    their next row from a queue when their episode ends (Monte Carlo episodes end anywhere between 100 and 1 500
-    steps).  Every row must equal the static one-episode-per-thread schedule bit for bit -- device tensors and host
-    buffers -- and the batch must actually be large enough to take the dynamic path."""
+    """BGR_CFG_DYNAMIC_SCHEDULE: a one-wave grid whose lanes pull their next row from a queue when their episode ends
+    (Monte Carlo episodes end anywhere between 100 and 1 500 steps).  Every row must equal the static
+    one-episode-per-thread schedule bit for bit -- device tensors and host buffers; the batch is larger than one wave
+    and ragged, so the queue runs dry in the middle of a warp."""
     import torch
     ta = bgr.tracks.skidpad(2048)
     track = bgr.Track.from_arrays(ta, cone_reach=4.0)
@@ -697,7 +697,7 @@ def test_dynamic_episode_scheduling_is_bit_identical(cuda_device, steer, accel, 
     dp, di = torch.from_numpy(params).to(cuda_device), torch.from_numpy(init).to(cuda_device)
     out = {}
     for static in (True, False):
-        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=1, static_schedule=static,
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=1, dynamic_schedule=not static,
                                 **noise)
         r = bgr.rollout(track, cfg, dp, di, aggregate=True)
         out[static] = (r.metrics.cpu().numpy(), r.status.cpu().numpy(), r.aggregate.cpu().numpy())
