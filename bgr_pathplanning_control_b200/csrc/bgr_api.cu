@@ -717,8 +717,8 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   bool attr_in_smem = true;
   if (!f64) {
     static const int force = [] { const char* e = std::getenv("BGR_ATTR_IN_SMEM"); return e ? std::atoi(e) : -1; }();
-    // (the full build is register-limited to 2 CTAs per SM: it can afford twice the shared memory per CTA)
-    attr_in_smem = force >= 0 ? force != 0 : plan->smem <= (full ? 2 * kSmemAllTablesLimit : kSmemAllTablesLimit);
+    // (the full build is register-limited to 3 CTAs per SM: it can afford 4/3 of the shared memory per CTA)
+    attr_in_smem = force >= 0 ? force != 0 : plan->smem <= (full ? kSmemAllTablesLimit * 4 / 3 : kSmemAllTablesLimit);
     if (!attr_in_smem) plan->smem = rollout_smem_bytes_xy_only(track->n_pad);
   }
   if (plan->smem > static_cast<size_t>(di.max_smem_optin)) {
