@@ -1083,7 +1083,10 @@ struct Pipeline {
   std::vector<cudaEvent_t> ev;   // [2 c] = upload of chunk c done, [2 c + 1] = kernel of chunk c done (re-recorded per call)
   Slot slot[kSlots];
   unsigned next = 0;
-  ~Pipeline() { release(); }
+  // No destructor on purpose: a thread_local destructor runs at thread / process exit, possibly after the CUDA runtime
+  // has begun to unload, where any CUDA call is undefined behaviour (observed: SIGSEGV at interpreter shutdown when
+  // worker threads owned a pipeline).  The streams and buffers of a thread's pipeline live until the process ends (the
+  // driver reclaims them); release() is for switching devices while the context is alive.
   void release() {
     if (device < 0) return;
     int prev = 0;

@@ -15,7 +15,8 @@
  *     returning, except: the opaque handles (track: with the LQG gain tables it caches on first use; MPC bank: with
  *     the candidate statistics it caches per cost configuration) and, per calling host thread, the host-buffer
  *     pipeline of bgr_rollout_host[_async] -- four internal streams, a pool of events and a ring of three device
- *     buffer sets sized for the largest batch seen (released when the thread exits) -- plus the CUDA event pair of
+ *     buffer sets sized for the largest batch seen (kept until the process ends: nothing is torn down from a
+ *     thread-exit destructor, where the CUDA runtime may already be unloading) -- plus the CUDA event pair of
  *     bgr_last_kernel_ms.
  *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are asynchronous on
  *     that stream unless the name ends in _host (those synchronise the stream before returning).
