@@ -29,7 +29,8 @@ cap() {  # <report name> <kernel regex> <skip> <bench args...>
 cap pp rollout_kernel 1 --workload pp_sweep
 cap stanley rollout_kernel 1 --workload stanley_lqg
 cap replan rollout_kernel 1 --workload pp_replan
-# config 5: the pure-pursuit kind is the launch that fills the GPU (kinds launch in the order stanley+lqg, stanley+pid, pp)
-cap mc "rollout_kernel_f32.*0.*0.*0.*1" 1 --workload skidpad_mc
+# config 5: the pure-pursuit kind is the launch that fills the GPU.  Kinds launch in the order stanley+lqg, stanley+pid,
+# pp, all instantiations of rollout_kernel_f32 (ncu matches base names): launch #6 is the pp kind of the first timed step
+cap mc rollout_kernel_f32 5 --workload skidpad_mc
 cap mpc mpc_factored_kernel 1 --workload mpc
 ls -la gpurun_out | head -60

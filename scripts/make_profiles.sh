@@ -33,8 +33,8 @@ summarise() {   # <report stem> <summary name> <listing stem> <mangled kernel> <
   python scripts/ncu_lines.py "$tmp/$1_src.csv" "$tmp/$3.txt" "$4" $5 60 "$out/opcodes_$2.json" > "$out/hot_lines_$2.txt"
   head -1 "$out/hot_lines_$2.txt"
 }
-summarise prof_pp pp_pid_kinematic bgr_rollout_inst_f32_lean _ZN3bgr18rollout_kernel_f32ILi0ELi0ELi0ELb0ELb1EEEvNS_11RolloutArgsE $steps
-summarise prof_stanley stanley_lqg_dynamic bgr_rollout_inst_f32_lean _ZN3bgr18rollout_kernel_f32ILi1ELi1ELi1ELb0ELb1EEEvNS_11RolloutArgsE $steps
+summarise prof_pp pp_pid_kinematic bgr_rollout_inst_f32_lean _ZN3bgr18rollout_kernel_f32ILi0ELi0ELi0ELb0ELb1ELb0EEEvNS_11RolloutArgsE $steps
+summarise prof_stanley stanley_lqg_dynamic bgr_rollout_inst_f32_lean _ZN3bgr18rollout_kernel_f32ILi1ELi1ELi1ELb0ELb1ELb0EEEvNS_11RolloutArgsE $steps
 # full-build kernels: units per launch from the bench line of the same workload (sim-steps actually executed)
 units() { python - "$1" "$2" <<'PY'
 import json, sys
@@ -45,8 +45,8 @@ except Exception:
     print(0)
 PY
 }
-summarise prof_replan pp_replan bgr_rollout_inst_f32_full _ZN3bgr18rollout_kernel_f32ILi0ELi0ELi0ELb1ELb1EEEvNS_11RolloutArgsE "$(units gpurun_out/plain_replan.log 1)"
-summarise prof_mc config5_pp bgr_rollout_inst_f32_full _ZN3bgr18rollout_kernel_f32ILi0ELi0ELi0ELb1ELb1EEEvNS_11RolloutArgsE 0
+summarise prof_replan pp_replan bgr_rollout_inst_f32_full _ZN3bgr18rollout_kernel_f32ILi0ELi0ELi0ELb1ELb1ELb0EEEvNS_11RolloutArgsE "$(units gpurun_out/plain_replan.log 1)"
+summarise prof_mc config5_pp bgr_rollout_inst_f32_full _ZN3bgr18rollout_kernel_f32ILi0ELi0ELi0ELb1ELb1ELb0EEEvNS_11RolloutArgsE 0
 if [ -f gpurun_out/prof_mpc.ncu-rep ]; then
   ncu -i gpurun_out/prof_mpc.ncu-rep --page raw --csv > "$tmp/mpc_raw.csv" 2> /dev/null
   python scripts/ncu_summary.py "$tmp/mpc_raw.csv" > "$out/ncu_full_mpc_factored.json"
@@ -80,7 +80,7 @@ fi
  cuobjdump -sass bgr_pathplanning_control_b200/libbgr_rollout.so \
    | grep -oE "UBLKCP\.S\.G|SYNCS\.[A-Z0-9.]+|CREDUX\.[A-Z]+|FADD2|FMUL2|FFMA2|MUFU\.SIN|MUFU\.COS|F2F\.[A-Z0-9.]+|HMMA[A-Z0-9.]*|UTC[A-Z0-9.]*MMA[A-Z0-9.]*" \
    | sort | uniq -c) > "$out/sass_evidence.txt"
-for k in ILi0ELi0ELi0ELb0ELb1:pp_pid_kinematic ILi1ELi1ELi1ELb0ELb1:stanley_lqg_dynamic; do
+for k in ILi0ELi0ELi0ELb0ELb1ELb0:pp_pid_kinematic ILi1ELi1ELi1ELb0ELb1ELb0:stanley_lqg_dynamic; do
   scripts/sass_kernel.sh bgr_pathplanning_control_b200/csrc/build/bgr_rollout_inst_f32_lean.o "rollout_kernel_f32${k%%:*}" "$out/sass_${k##*:}.txt" > /dev/null
   python - "$out/sass_${k##*:}.txt" <<'PY'
 import re, sys
