@@ -643,15 +643,21 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
             assert int(s_all[:, abi.S_STEPS].to(torch.int64).sum().item()) == int(round(total_steps / steps))
         del m_all, s_all
     # e2e: host buffers (one persistent host thread per kind through bgr_rollout_host)
+    # (result buffers pinned like the inputs: a download into pageable memory goes through the driver's staging buffer
+    #  and blocks the host thread that issued it)
+    h_outs = [bgr.RolloutResult(torch.empty((per, abi.N_METRICS), dtype=torch.float32).pin_memory().numpy(),
+                                torch.empty((per, abi.N_STATUS), dtype=torch.int32).pin_memory().numpy(), None, None)
+              for _ in jobs]
     for _ in range(2):      # (the worker threads build their copy / compute pipelines on first use)
-        bgr.rollout_groups(track, [(j[0], j[4], j[5]) for j in jobs], aggregate=True, order=[2, 1, 0])
+        bgr.rollout_groups(track, [(j[0], j[4], j[5]) for j in jobs], aggregate=True, outs=h_outs, order=[2, 1, 0])
     w0 = time.perf_counter()
     e2e_steps = 0.0
     for _ in range(steps):
         if serial:
-            rs = [bgr.rollout(track, j[0], j[4], j[5], aggregate=True) for j in jobs]
+            rs = [bgr.rollout(track, j[0], j[4], j[5], aggregate=True, out=o) for j, o in zip(jobs, h_outs)]
         else:
-            rs = bgr.rollout_groups(track, [(j[0], j[4], j[5]) for j in jobs], aggregate=True, order=[2, 1, 0])
+            rs = bgr.rollout_groups(track, [(j[0], j[4], j[5]) for j in jobs], aggregate=True, outs=h_outs,
+                                    order=[2, 1, 0])
         e2e_steps += sum(float(r.aggregate[abi.A_STEPS]) for r in rs)
     e2e_s = time.perf_counter() - w0
     e2e_value = ctx.reduce(e2e_steps, "SUM") / ctx.reduce(e2e_s, "MAX")

@@ -161,13 +161,20 @@ constexpr int kMaxRivals = 1024;   // longer lists fall back to the exact scan (
 // for p in slab(j) with |p - w_j| < guard_twin(j) the exact argmin is the best of j and the twin triple -- three
 // evaluations from shared memory instead of a walk through the sorted rival list.  Same exactness argument as the
 // guard itself (only the excluded set is larger, and it is evaluated exhaustively).
+//
+// Layout of rival_list: every list starts at an EVEN entry (the fp32 kernel reads entries in pairs, one 16-byte load)
+// and is followed by two or three SENTINEL entries (waypoint 0, reach-in distance +inf) such that the pair after the
+// last pair holding a real entry starts with a sentinel: the device loop needs no count, it stops at the first entry
+// the car is too close to w_j for -- at the latest the sentinel.  rival_range[j] = (first entry, number of REAL
+// entries), count < 0: no usable list.  One more sentinel pair closes the array (the loop loads one pair ahead).
 static void compute_guards(const std::vector<double>& x, const std::vector<double>& y, bool closed,
-                           std::vector<double>* guard, std::vector<int32_t>* rival_first,
+                           std::vector<double>* guard, std::vector<int2>* rival_range,
                            std::vector<int2>* rival_list, std::vector<int2>* twin) {
   const int n = static_cast<int>(x.size());
+  const int2 sentinel = make_int2(0, 0x7f800000);
   twin->assign(n, make_int2(-1, 0));
   guard->assign(n, 0.0);
-  rival_first->assign(n + 1, 0);
+  rival_range->assign(n, make_int2(0, -1));
   rival_list->clear();
   const double reach2 = kRivalReach * kRivalReach;
   std::vector<std::pair<double, int32_t>> mine;   // (squared reach-in distance, waypoint)
@@ -228,8 +235,8 @@ static void compute_guards(const std::vector<double>& x, const std::vector<doubl
       }
     }
     (*guard)[j] = std::sqrt(best2);  // may be +inf (e.g. a straight line)
-    (*rival_first)[j] = static_cast<int32_t>(rival_list->size());
     if (lists_ok) {
+      (*rival_range)[j] = make_int2(static_cast<int>(rival_list->size()), static_cast<int>(mine.size()));
       // sorted by the distance from w_j at which the rival can first win: the device walks a list only up to the
       // car's own distance from w_j (stored 1e-4 m short, which covers the fp32 rounding of waypoints and offsets)
       std::sort(mine.begin(), mine.end());
@@ -253,10 +260,13 @@ static void compute_guards(const std::vector<double>& x, const std::vector<doubl
         const float c2 = std::nextafterf(static_cast<float>(c * c), 0.0f);
         rival_list->push_back(make_int2(m.second, __builtin_bit_cast(int, c2)));
       }
+      if (mine.size() % 2 != 0) rival_list->push_back(sentinel);
+      rival_list->push_back(sentinel);
+      rival_list->push_back(sentinel);
     }
-    else (*rival_first)[j] = -static_cast<int32_t>(rival_list->size()) - 1;   // negative: no usable list here
   }
-  (*rival_first)[n] = static_cast<int32_t>(rival_list->size());
+  rival_list->push_back(sentinel);
+  rival_list->push_back(sentinel);
 }
 
 }  // namespace bgr
@@ -457,10 +467,10 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     }
     t->path_yaw[j] = std::atan2(dy, dx);
   }
-  std::vector<int32_t> rival_first;
+  std::vector<int2> rival_range;
   std::vector<int2> rival_list;
   std::vector<int2> twin;
-  compute_guards(t->x, t->y, t->closed != 0, &t->guard_radius, &rival_first, &rival_list, &twin);
+  compute_guards(t->x, t->y, t->closed != 0, &t->guard_radius, &rival_range, &rival_list, &twin);
   for (const auto& tw : twin) t->twin_count += tw.x >= 0 ? 1 : 0;
 
   t->ds_min = INFINITY;
@@ -477,6 +487,8 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     std::sort(g.begin(), g.end());
     t->guard_min = g.front();
     t->guard_median = g[g.size() / 2];
+    t->guard_tight_frac = static_cast<double>(std::lower_bound(g.begin(), g.end(), kTightGuard) - g.begin()) /
+                          static_cast<double>(g.size());
   }
 
   std::vector<float2> xy_f(n_pad);
@@ -499,22 +511,15 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     guard2[j] = static_cast<float>(std::min(g * g, 1e30));
   }
 
-  // rival lists as (first, count) per waypoint; count < 0 = no usable list (exact scan instead)
-  std::vector<int2> rival_range(n);
+  // rival lists: (first, count) per waypoint; count < 0 = no usable list (exact scan instead)
   for (int j = 0; j < n; ++j) {
-    const bool ok = rival_first[j] >= 0;
-    const int first = ok ? rival_first[j] : -rival_first[j] - 1;
-    int next = rival_first[j + 1];
-    if (next < 0) next = -next - 1;
-    rival_range[j] = make_int2(first, ok ? next - first : -1);
-    if (ok) {
-      t->rival_total += next - first;
-      t->rival_max = std::max(t->rival_max, next - first);
+    if (rival_range[j].y >= 0) {
+      t->rival_total += rival_range[j].y;
+      t->rival_max = std::max(t->rival_max, rival_range[j].y);
     } else {
       ++t->rival_unlisted;
     }
   }
-  if (rival_list.empty()) rival_list.push_back(make_int2(0, 0));
 
   // cone candidate lists: cones within cone_reach of waypoint j
   std::vector<int32_t> cone_range(n, 0), cone_list;
@@ -790,6 +795,14 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   A.cones_on = cones_on ? 1 : 0;
   A.attr_in_smem = attr_in_smem ? 1 : 0;
   A.noise_on = noise_on ? 1 : 0;
+  // With pose noise, or on a track that mostly runs inside a tight guard (the skidpad's circles are driven twice: 90 % of
+  // its waypoints), some lane of nearly every warp leaves the five-point window of the nearest search, so the warp pays
+  // for the window AND the complete search: go to the complete search directly.  Same result either way.
+  A.search_direct = (noise_on || track->guard_tight_frac > 0.25) ? 1 : 0;
+  {   // (diagnostic override: BGR_SEARCH_DIRECT=0 / 1)
+    static const int force = [] { const char* e = std::getenv("BGR_SEARCH_DIRECT"); return e ? std::atoi(e) : -1; }();
+    if (force >= 0) A.search_direct = force != 0;
+  }
   A.phases = sp.phases;
   A.ctrl_in = sp.ctrl_in;
   A.ctrl_out = sp.ctrl_out;

@@ -20,6 +20,7 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kTwoPi = 2.0 * 3.14159265358979323846;
 constexpr int kRolloutThreads = 256;
 constexpr double kRivalReach = 2.5;                                   // [m] rival lists are complete up to here (host)
+constexpr double kTightGuard = 0.5;                                   // [m] a guard below this counts as tight (host: search_direct)
 constexpr double kRivalAccept = kRivalReach * (1.0 - 1e-4) - 1e-4;   // [m] ... and trusted up to here (device)
 
 struct alignas(32) D4 {
@@ -118,6 +119,8 @@ struct RolloutArgs {
   int32_t cones_on;
   int32_t attr_in_smem;   // fp32 kernels: attr / guard tables staged in shared memory (short tracks) or read via L1
   int32_t noise_on;
+  int32_t search_direct;  // fp32 full build: skip the five-point window of the nearest search and run the complete search
+                          // straight away (host: pose noise on, or most of the track inside a tight exactness guard)
   // single-step plumbing (EXTRAS kernels only; all nullptr for a rollout)
   int32_t phases;
   const double* ctrl_in;   // [E][BGR_N_CTRL]

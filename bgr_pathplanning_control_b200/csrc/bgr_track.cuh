@@ -36,6 +36,7 @@ struct bgr_track {
   // host copies
   std::vector<double> x, y, kappa, path_yaw, guard_radius;
   double ds_min = 0, ds_max = 0, guard_min = 0, guard_median = 0;
+  double guard_tight_frac = 0;     // share of waypoints whose exactness guard is under kTightGuard (lines driven twice, crossings)
   long long rival_total = 0;
   int rival_max = 0, rival_unlisted = 0, twin_count = 0;
 
