@@ -46,6 +46,7 @@ MAX_CONES = 512
 CFG_AUDIT = 1
 CFG_STANLEY_SHADOWED = 2
 CFG_DYNAMIC_SCHEDULE = 4
+CFG_KEEP_ORDER = 8
 MPC_EXPLICIT_ROLLOUT = 1
 PHASE_STEER, PHASE_ACCEL, PHASE_MODEL, PHASE_ERRORS, PHASE_KAPPA_GIVEN = 1, 2, 4, 8, 16
 CMD_STEER, CMD_ACCEL, CMD_KAPPA = 0, 1, 2

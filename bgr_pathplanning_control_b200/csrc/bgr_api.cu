@@ -697,7 +697,10 @@ struct Plan {
   // dynamic episode scheduling (full fp32 build, plain rollouts): one wave of CTAs pulls rows from a device counter
   bool dynamic = false;
   long long wave_dyn = 0;
+  // launch order by target speed (bgr_misc.cu): ranges of at least kOrderMin episodes that can end early
+  bool order = false;
 };
+constexpr long long kOrderMin = 4096;
 
 // Validate the configuration, fill the kernel arguments that do not depend on the episode range, pick the kernel
 // specialisation and make sure the LQG tables are resident (cached on the track handle).
@@ -864,6 +867,12 @@ int make_plan(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, const Step
   // per-step cost, not by stragglers -- so it is opt-in.
   plan->dynamic = (cfg->flags & BGR_CFG_DYNAMIC_SCHEDULE) != 0 && full && !f64 && sp.ctrl_in == nullptr &&
                   !sp.force_full && cfg->split_steps == 0;
+  // Launch order by target speed: for rollouts that can end before the step cap for a reason that scales with the speed
+  // (end of an open path, lap target) -- a warp then holds episodes of like length.  Plain fp32 rollouts only; the
+  // output rows are the same either way (BGR_CFG_KEEP_ORDER switches it off).
+  plan->order = (cfg->flags & BGR_CFG_KEEP_ORDER) == 0 && !f64 && !plan->dynamic && sp.ctrl_in == nullptr &&
+                sp.params64 == nullptr && !sp.force_full && cfg->split_steps == 0 &&
+                (track->closed == 0 || cfg->laps_target > 0);
   if (plan->dynamic) {
     RolloutArgs Q = A;
     Q.queue = reinterpret_cast<int32_t*>(uintptr_t(16));   // (only selects the instantiation: nothing is launched)
@@ -914,6 +923,12 @@ int launch_rollout_phases(const Plan& plan, int split_steps, long long id_offset
                           const double* d_init, float* d_metrics, int32_t* d_status, double* d_traj, int32_t* d_work,
                           cudaStream_t stream, int32_t* d_queue = nullptr) {
   const int S = plan.A.max_steps;
+  if (plan.order && d_work != nullptr && count >= kOrderMin) {
+    // d_work = int32[count + kOrderBuckets]: the launch order, then the bucket counters
+    BGR_CUDA(launch_order_by_speed(d_params, count, d_work, d_work + count, stream));
+    count_launch(3);
+    return launch_range(plan, id_offset, count, d_params, d_init, d_metrics, d_status, d_traj, S, d_work, nullptr, stream);
+  }
   if (split_steps <= 0 || split_steps >= S || d_work == nullptr)
     return launch_range(plan, id_offset, count, d_params, d_init, d_metrics, d_status, d_traj, S, nullptr, nullptr, stream,
                         d_queue);
@@ -987,6 +1002,9 @@ int rollout_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, int64_t
   if (split > 0 && split < cfg->max_steps)
     BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_work), static_cast<size_t>(n_episodes + 1) * sizeof(int32_t),
                              stream));
+  else if (plan.order && n_episodes >= kOrderMin)
+    BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_work),
+                             static_cast<size_t>(n_episodes + kOrderBuckets) * sizeof(int32_t), stream));
   int32_t* d_queue = nullptr;
   if (plan.dynamic && n_episodes > plan.wave_dyn)
     BGR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_queue), sizeof(int32_t), stream));
@@ -1245,7 +1263,7 @@ int rollout_host_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, in
   BGR_TRY(ensure_chunk_events(chunks.size()));
   Slot* sl = nullptr;
   BGR_TRY(acquire_slot(E, h_aggregate != nullptr ? static_cast<size_t>(grid_total) : 0,
-                       two_phase ? E + chunks.size() + 64 : 0, &sl));
+                       two_phase ? E + chunks.size() + 64 : plan.order ? E + chunks.size() * kOrderBuckets : 0, &sl));
   // the trajectory dump (a debugging aid, synchronous calls only) is the one stream-ordered allocation left
   Scratch sc(stream);
   double* d_traj = nullptr;
@@ -1286,7 +1304,8 @@ int rollout_host_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, in
                                   sl->d_init + o * BGR_N_STATE, sl->d_metrics + o * BGR_N_METRICS,
                                   sl->d_status + o * BGR_N_STATUS,
                                   d_traj != nullptr ? d_traj + o * S * BGR_N_TRAJ : nullptr,
-                                  two_phase ? sl->d_work + o + c : nullptr, cs,
+                                  two_phase ? sl->d_work + o + c : plan.order ? sl->d_work + o + c * kOrderBuckets : nullptr,
+                                  cs,
                                   c < static_cast<size_t>(kMaxQueueChunks) ? sl->d_queue + c : nullptr));
     if (last) {
       BGR_CUDA(cudaEventRecord(g_last.stop, cs));

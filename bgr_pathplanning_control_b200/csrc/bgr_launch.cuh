@@ -79,6 +79,10 @@ cudaError_t launch_aggregate_partials(const float* metrics, const int32_t* statu
                                       double* partials, cudaStream_t stream);
 cudaError_t launch_compact_survivors(const int32_t* status, long long n_episodes, int32_t* idx, int32_t* count,
                                      cudaStream_t stream);
+// launch order by target speed: perm[count] = the rows, slowest first; hist = kOrderBuckets ints of scratch
+constexpr int kOrderBuckets = 32768;
+cudaError_t launch_order_by_speed(const float* params, long long n_episodes, int32_t* perm, int32_t* hist,
+                                  cudaStream_t stream);
 cudaError_t launch_fp32_probe(float* out, int grid, int iters, cudaStream_t stream);
 cudaError_t launch_fp64_probe(double* out, int grid, int iters, cudaStream_t stream);
 

@@ -102,6 +102,80 @@ cudaError_t launch_compact_survivors(const int32_t* status, long long n_episodes
   return cudaGetLastError();
 }
 
+// ---- launch order by target speed (bucket sort) ----
+// An episode that stops at the end of the path or at a lap target runs for about (path length) / (target speed) steps, and
+// a warp runs until its slowest lane is done: with speeds drawn at random, a quarter of the lane-steps of BASELINE config 5
+// belong to lanes that have already finished.  Launching the episodes in order of target speed puts lanes of like length
+// into one warp (and, since they also travel together, into the same branch of the step at the same time).  Only the
+// launch order changes: thread t works on row perm[t] and writes row perm[t]; an episode is a function of its own row.
+// Key = the upper 16 bits of the speed's float pattern (sign, exponent, 7 mantissa bits: 1/128 relative resolution);
+// slowest first, so the longest episodes start first and the short ones fill the tail.  The order inside a bucket is
+// whatever the atomics give -- results do not depend on it.
+__device__ __forceinline__ int order_bucket(const float* __restrict__ params, long long e) {
+  const unsigned bits = __float_as_uint(params[e * BGR_N_PARAMS + BGR_P_TARGET_SPEED]);
+  return static_cast<int>(min(bits >> 16, static_cast<unsigned>(kOrderBuckets - 1)));   // (negative / NaN: last bucket)
+}
+
+__global__ void __launch_bounds__(256) order_hist_kernel(const float* __restrict__ params, long long n_episodes,
+                                                         int32_t* __restrict__ hist) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e < n_episodes) atomicAdd(hist + order_bucket(params, e), 1);
+}
+
+// one CTA of 1024 threads: exclusive prefix sum of the kOrderBuckets counters, in place (they become the write cursors)
+__global__ void __launch_bounds__(1024) order_scan_kernel(int32_t* __restrict__ hist) {
+  constexpr int kPer = kOrderBuckets / 1024;
+  __shared__ int warp_sums[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  int v[kPer], sum = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    v[i] = hist[t * kPer + i];
+    sum += v[i];
+  }
+  int inc = sum;                                      // inclusive scan of the per-thread sums across the warp ...
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  if (w == 0) {                                       // ... and of the warp totals across the CTA
+    int ws = warp_sums[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, ws, d);
+      if (lane >= d) ws += o;
+    }
+    warp_sums[lane] = ws;
+  }
+  __syncthreads();
+  int run = inc - sum + (w > 0 ? warp_sums[w - 1] : 0);
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    hist[t * kPer + i] = run;
+    run += v[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) order_scatter_kernel(const float* __restrict__ params, long long n_episodes,
+                                                            int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e < n_episodes) perm[atomicAdd(cursor + order_bucket(params, e), 1)] = static_cast<int32_t>(e);
+}
+
+cudaError_t launch_order_by_speed(const float* params, long long n_episodes, int32_t* perm, int32_t* hist,
+                                  cudaStream_t stream) {
+  cudaError_t err = cudaMemsetAsync(hist, 0, kOrderBuckets * sizeof(int32_t), stream);
+  if (err != cudaSuccess) return err;
+  const unsigned grid = static_cast<unsigned>((n_episodes + 255) / 256);
+  order_hist_kernel<<<grid, 256, 0, stream>>>(params, n_episodes, hist);
+  order_scan_kernel<<<1, 1024, 0, stream>>>(hist);
+  order_scatter_kernel<<<grid, 256, 0, stream>>>(params, n_episodes, hist, perm);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_reduce_partials(const double* partials, int n_blocks, double* out, cudaStream_t stream) {
   reduce_partials_kernel<<<1, 32 * BGR_N_AGG, 0, stream>>>(partials, n_blocks, out);
   return cudaGetLastError();

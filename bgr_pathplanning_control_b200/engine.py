@@ -116,6 +116,7 @@ class RolloutConfig:
     laps_target: int = 0
     audit: bool = False              # fill the near-tie audit channel (full kernel build)
     dynamic_schedule: bool = False   # full build, > 1 wave of episodes: lanes pull their next episode from a queue
+    keep_order: bool = False         # launch in row order (default: rollouts that can end early launch slowest-first)
     dt: float = conf.dt
     wheelbase: float = conf.WB
     l_f: float = conf.l_f
@@ -153,7 +154,8 @@ class RolloutConfig:
             raise ValueError(f"Unknown controller / model / precision: {e.args[0]}") from None
         c.max_steps, c.laps, c.laps_target = int(self.max_steps), int(self.laps), int(self.laps_target)
         c.flags = ((abi.CFG_AUDIT if self.audit else 0) | (abi.CFG_STANLEY_SHADOWED if self.stanley_shadowed else 0)
-                   | (abi.CFG_DYNAMIC_SCHEDULE if self.dynamic_schedule else 0))
+                   | (abi.CFG_DYNAMIC_SCHEDULE if self.dynamic_schedule else 0)
+                   | (abi.CFG_KEEP_ORDER if self.keep_order else 0))
         c.stanley_max_steer_rate, c.stanley_alpha = float(self.stanley_max_steer_rate), float(self.stanley_alpha)
         c.stanley_lookahead = float(self.stanley_lookahead)
         for k in ("dt", "wheelbase", "l_f", "l_r", "max_steer", "max_accel", "max_decel", "hit_radius", "tie_eps",

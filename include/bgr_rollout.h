@@ -184,6 +184,12 @@ typedef struct bgr_track_info {
                            thread.  For batches with heavy-tailed episode lengths; output rows are bit-identical either
                            way.  Off by default (measured neutral on BASELINE config 5). */
 
+#define BGR_CFG_KEEP_ORDER 8 /* fp32 rollouts that can end before the step cap (open path, lap target) launch their
+                           episodes in order of target speed, slowest first, so that a warp holds episodes of like length
+                           (a bucket sort of the rows' BGR_P_TARGET_SPEED on the device, part of the call).  Thread t then
+                           works on row perm[t]; every output row is the same as without it.  This bit keeps the launch
+                           in row order. */
+
 typedef struct bgr_rollout_cfg {
   int32_t steer_kind, accel_kind, model_kind, precision;
   int32_t max_steps;       /* step cap (legacy loop: T / dt, old/animation_loop.py:16-17,71) */

@@ -710,3 +710,58 @@ def test_dynamic_episode_scheduling_is_bit_identical(cuda_device, steer, accel, 
     steps = out[True][1][:, abi.S_STEPS]
     assert steps.min() >= 1 and steps.max() > 3 * steps.mean() or steer == "pure_pursuit"    # heavy-tailed lengths
 
+
+
+@pytest.mark.parametrize("steer,accel,model,clean", [("pure_pursuit", "pid", "kinematic", False),
+                                                     ("pure_pursuit", "pid", "kinematic", True),
+                                                     ("stanley", "pid", "kinematic", False),
+                                                     ("stanley", "lqg", "dynamic", False)])
+def test_launch_order_by_speed_is_bit_identical(cuda_device, steer, accel, model, clean):
+    """Rollouts that can end early (open path, lap target) launch their episodes in order of target speed (a device
+    bucket sort; thread t works on row perm[t]).  Every output row must equal the row-order launch (BGR_CFG_KEEP_ORDER)
+    bit for bit -- full build with noise and cones, lean build without, device tensors and host buffers (whose chunks
+    are ordered one by one), and a batch that is ragged against both the CTA and the bucket-scan width."""
+    import torch
+    ta = bgr.tracks.skidpad(2048)
+    track = bgr.Track.from_arrays(ta, cone_reach=4.0)
+    E = 148 * 3 * 256 + 20011                      # more than one wave (host path: several chunks), ragged
+    noise = {} if clean else dict(sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1, sigma_cone=0.05, noise_seed=11,
+                                  hit_radius=0.5, episode_id_base=4321)
+    params = bgr.sweeps.monte_carlo_params(E, start=99)
+    params[::1000, abi.P_TARGET_SPEED] = 0.0        # a few degenerate keys (bucket 0) ...
+    params[1::1000, abi.P_TARGET_SPEED] = 1e30      # ... and a very large one
+    init = bgr.initial_states(ta, E, index=0, v0=5.0 if model == "dynamic" else 0.0)
+    init[:, abi.YAW] = 0.0
+    dp, di = torch.from_numpy(params).to(cuda_device), torch.from_numpy(init).to(cuda_device)
+    out = {}
+    for keep in (True, False):
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=1, keep_order=keep, **noise)
+        n0 = bgr.launch_count()
+        r = bgr.rollout(track, cfg, dp, di, aggregate=True)
+        launches = bgr.launch_count() - n0
+        assert launches == (3 if keep else 6)      # step kernel + 2 aggregate kernels (+ histogram, scan, scatter)
+        out[keep] = (r.metrics.cpu().numpy(), r.status.cpu().numpy(), r.aggregate.cpu().numpy())
+        host = bgr.rollout(track, cfg, params, init, aggregate=True)
+        assert np.array_equal(host.metrics, out[keep][0], equal_nan=True) and np.array_equal(host.status, out[keep][1])
+    assert np.array_equal(out[True][0], out[False][0], equal_nan=True)
+    assert np.array_equal(out[True][1], out[False][1])
+    # (the aggregate is a fixed-order reduction over the ROWS, so it is identical too)
+    assert np.array_equal(out[True][2], out[False][2], equal_nan=True)
+    steps = out[True][1][:, abi.S_STEPS]
+    assert steps.max() > 1.2 * np.median(steps)     # the lengths do differ: the order matters for the schedule
+
+
+def test_launch_order_small_batches_and_closed_tracks_keep_row_order(cuda_device):
+    """Below 4 096 episodes, and on rollouts that cannot end early for a speed-dependent reason (closed track without a
+    lap target), the launch stays in row order: no extra kernels."""
+    import torch
+    for ta, E, laps_target, extra in ((bgr.tracks.skidpad(2048), 1024, 0, 0), (bgr.tracks.stadium_oval(1024), 8192, 0, 0),
+                                      (bgr.tracks.stadium_oval(1024), 8192, 1, 3)):
+        track = bgr.Track.from_arrays(ta)
+        cfg = bgr.RolloutConfig(steer="pure_pursuit", accel="pid", model="kinematic", max_steps=400, laps=2,
+                                laps_target=laps_target)
+        p = torch.from_numpy(bgr.sweeps.monte_carlo_params(E)).to(cuda_device)
+        s = torch.from_numpy(bgr.initial_states(ta, E)).to(cuda_device)
+        n0 = bgr.launch_count()
+        bgr.rollout(track, cfg, p, s)
+        assert bgr.launch_count() - n0 == 1 + extra
