@@ -576,12 +576,23 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
             noise["hit_radius"] = 0.0
         elif k == "pose_noise":
             noise.update(sigma_xy=0.0, sigma_yaw=0.0, sigma_v=0.0)
-    jobs = []
+    jobs, dynamic = [], []
     for g, (steer, accel, model) in enumerate(kinds):
         lo = (rank * len(kinds) + g) * per
-        split = max(0, int(os.environ.get("BGR_MC_SPLIT", "0")))
+        # diagnostics: BGR_MC_SPLIT=<steps> (two-phase run), BGR_MC_DYNAMIC=1 (dynamic schedule), both for the kinds
+        # listed in BGR_MC_KINDS (default: all), e.g. BGR_MC_KINDS=1,2 = the two Stanley kinds
+        on = str(g) in os.environ.get("BGR_MC_KINDS", "0,1,2").split(",")
+        split = max(0, int(os.environ.get("BGR_MC_SPLIT", "0"))) if on else 0
+        # Schedules (rows are bit-identical under all of them): the pure-pursuit episodes end where the path ends, after
+        # 746 .. 1 241 steps depending on their target speed -- the library launches them slowest-first on its own.  The
+        # noisy Stanley episodes end at the first crossing (99.7 % within 160 steps) or, for one in 400 .. 2 500, run on
+        # for up to 1 500 steps: heavy-tailed and unpredictable, the case the dynamic schedule exists for.
+        dyn = steer == "stanley"
+        if "BGR_MC_DYNAMIC" in os.environ:
+            dyn = on and os.environ["BGR_MC_DYNAMIC"] == "1"
+        dynamic.append(dyn)
         cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=S, laps=1, episode_id_base=lo,
-                                split_steps=split, dynamic_schedule=os.environ.get("BGR_MC_DYNAMIC") == "1", **noise)
+                                split_steps=split, dynamic_schedule=dyn, **noise)
         init = bgr.initial_states(ta, per, index=0, v0=5.0 if model == "dynamic" else 0.0)
         init[:, abi.YAW] = 0.0
         params = bgr.sweeps.monte_carlo_params(per, start=lo)
@@ -679,8 +690,8 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
                    "cone_hits_last_step_rank0": hits, "parallelism": f"episode sharding x{world}",
                    "launch": "kinds back to back on one stream" if serial else
                              "kinds on three concurrent streams, latency-bound Stanley kinds first",
-                   "schedule": "dynamic (one-wave grids; lanes pull their next episode from a queue)"
-                               if os.environ.get("BGR_MC_DYNAMIC") == "1" else "static (one episode per thread)",
+                   "schedule": ["dynamic (one-wave grid; lanes pull their next episode from a queue)" if d else
+                                "static, launched in order of target speed (slowest first)" for d in dynamic],
                    "l2": "state lives in registers; 112 B in + 88 B out per episode"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per * len(kinds) * 112,
