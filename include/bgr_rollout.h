@@ -107,7 +107,8 @@ extern "C" {
 #define BGR_S_LAPS 5
 #define BGR_S_NEAR_TIES 6    /* steps with a threshold decision closer than tie_eps (audit channel) */
 #define BGR_S_FIRST_TIE 7    /* first such step, -1 if none */
-#define BGR_S_FALLBACKS 8    /* steps that needed the exact global nearest scan */
+#define BGR_S_FALLBACKS 8    /* nearest searches that needed the exact global scan (fp32 kernels: an episode's first
+                                search descends from waypoint 0 and only scans when that takes more than 16 moves) */
 #define BGR_N_STATUS 10
 
 #define BGR_ST_PATH_END 1
