@@ -783,10 +783,30 @@ def run_mpc(ctx, steps, warmup, E=16384, K=4096, H=30):
         w0 = time.perf_counter()
         for _ in range(n_e2e):
             bgr.mpc_evaluate(track, cfg, p_states, p_ref, hbank, out=p_out)
+        e2e_sync_s = (time.perf_counter() - w0) / n_e2e
+        # ... and the streaming form: two sets of pinned result buffers, batch i + 1 queued before batch i is read
+        # (bgr_mpc_eval_bank_host_async): the upload of one batch runs under the kernels of the other
+        p_out2 = [p_out, bgr.MpcResult(torch.empty((E, 2), dtype=torch.float32).pin_memory().numpy(),
+                                       torch.empty(E, dtype=torch.float32).pin_memory().numpy(),
+                                       torch.empty(E, dtype=torch.int32).pin_memory().numpy())]
+        p_in2 = [(p_states, p_ref), (torch.from_numpy(states).pin_memory().numpy(), torch.from_numpy(ref_start).pin_memory().numpy())]
+        for i in range(4):
+            bgr.mpc_evaluate_async(track, cfg, *p_in2[i & 1], hbank, out=p_out2[i & 1]).wait()
+        assert np.array_equal(p_out2[1].best_idx, res.best_idx.cpu().numpy())
+        w0 = time.perf_counter()
+        pend = bgr.mpc_evaluate_async(track, cfg, *p_in2[0], hbank, out=p_out2[0])
+        for i in range(1, n_e2e):
+            nxt = bgr.mpc_evaluate_async(track, cfg, *p_in2[i & 1], hbank, out=p_out2[i & 1])
+            got = pend.wait()
+            _ = got.best_u[0, 0]                      # (the step's result is read on the host)
+            pend = nxt
+        pend.wait()
         e2e_s = (time.perf_counter() - w0) / n_e2e
-        e2e_api = "bgr_mpc_eval_bank_host (pinned numpy states in, commands out, resident candidate bank)"
+        e2e_api = ("bgr_mpc_eval_bank_host_async (pinned numpy states in, commands out, resident candidate bank; batch "
+                   "i + 1 queued before batch i is read)")
         h2d_step = states.nbytes + ref_start.nbytes
     except AttributeError:
+        e2e_sync_s = None
         n_e2e = max(steps, 20)
         w0 = time.perf_counter()
         for _ in range(n_e2e):
@@ -834,7 +854,12 @@ def run_mpc(ctx, steps, warmup, E=16384, K=4096, H=30):
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "candidate-steps/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": E * 16,
                 "api": e2e_api, "frac_of_value": e2e / value,
-                "frac_of_one_call_per_step": e2e / (units_step * world / (ms_call * 1e-3))},
+                "frac_of_one_call_per_step": e2e / (units_step * world / (ms_call * 1e-3)),
+                # the same batches one synchronous call at a time (bgr_mpc_eval_bank_host): upload, three kernels and
+                # download in sequence -- the latency of ONE control period, which a closed loop cannot overlap
+                "synchronous": None if e2e_sync_s is None else
+                {"value": units_step * world / e2e_sync_s, "ms_per_call": e2e_sync_s * 1e3,
+                 "api": "bgr_mpc_eval_bank_host (rank 0's own clock)"}},
         "gpu_launches": int(timed_launches),
         "roofline": roof,
     }

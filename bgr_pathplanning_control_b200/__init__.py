@@ -7,12 +7,20 @@ Layout: ``csrc/`` sm_100a CUDA kernels + the C ABI (``include/bgr_rollout.h``); 
 synthetic inputs;  ``sharding.py`` multi-GPU plumbing;  ``roofline.py`` the frozen flop/byte counts.
 Importing the package does not load the CUDA library; the first call does and raises if it is not built.
 """
+import os as _os
+
+# More hardware work queues than the default 8: the host-buffer pipelines use four streams per host thread, and streams
+# that share a queue wait for each other's event waits (measured: a mixed-controller group of three host threads ran
+# its kernels one after the other).  Only effective when set before the process creates its CUDA context; an explicit
+# setting of the variable wins.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from . import _abi, tracks, sweeps, sharding, roofline          # noqa: F401
 from .vehicle_config import Vehicle_config, conf               # noqa: F401
 from .engine import (Track, RolloutConfig, RolloutResult, MpcConfig, MpcResult, rollout, rollout_groups, mpc_evaluate,   # noqa: F401
                      default_params, initial_states, candidate_bank, lqg_design, lqg_covariance, fp32_peak_probe,
                      last_kernel_ms, launch_count, identify_dynamics, rollout_async, PendingRollout, build_id,
-                     release_group_streams, MpcBank, fp64_peak_probe)
+                     release_group_streams, MpcBank, fp64_peak_probe, mpc_evaluate_async, PendingMpc)
 from .controllers import (PurePursuitController, StanleyController, ShadowedStanleyController, AccelerationPIDController,            # noqa: F401
                           LQGAccelerationController, MPCController, get_steering_controller,
                           normalize_angle, find_target_point, compute_control_commands)

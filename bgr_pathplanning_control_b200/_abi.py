@@ -64,7 +64,7 @@ EXPORTS = (
     "bgr_track_create", "bgr_track_destroy", "bgr_track_info", "bgr_track_tables",
     "bgr_rollout", "bgr_rollout_host", "bgr_rollout_host_async", "bgr_step_host", "bgr_lqg_design", "bgr_lqg_covariance",
     "bgr_mpc_eval", "bgr_mpc_eval_host", "bgr_mpc_bank_create", "bgr_mpc_bank_destroy", "bgr_mpc_eval_bank",
-    "bgr_mpc_eval_bank_host", "bgr_identify_dynamics", "bgr_identify_dynamics_host",
+    "bgr_mpc_eval_bank_host", "bgr_mpc_eval_bank_host_async", "bgr_identify_dynamics", "bgr_identify_dynamics_host",
     "bgr_fp32_peak_probe", "bgr_fp64_peak_probe", "bgr_last_kernel_ms", "bgr_launch_count",
 )
 
@@ -174,6 +174,8 @@ def load():
     lib.bgr_mpc_eval_bank.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bgr_mpc_eval_bank_host.restype = C.c_int
     lib.bgr_mpc_eval_bank_host.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bgr_mpc_eval_bank_host_async.restype = C.c_int
+    lib.bgr_mpc_eval_bank_host_async.argtypes = [vp, C.POINTER(MpcCfg), i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bgr_fp64_peak_probe.restype = C.c_int
     lib.bgr_fp64_peak_probe.argtypes = [C.c_int, vp]
     lib.bgr_identify_dynamics.restype = C.c_int

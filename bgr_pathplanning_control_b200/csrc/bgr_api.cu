@@ -1261,7 +1261,15 @@ int rollout_host_impl(const bgr_track_t* track, const bgr_rollout_cfg_t* cfg, in
   const bool two_phase = cfg->split_steps > 0 && static_cast<int>(cfg->split_steps) < cfg->max_steps;
   // a dynamically scheduled kernel wants MANY episodes per launch (its lanes refill from the queue): four waves per
   // chunk instead of one
-  const std::vector<long long> chunks = host_chunks(n_episodes, plan.dynamic ? 4 * plan.wave_dyn : plan.wave);
+  // Rollouts whose episodes end at different times (speed-ordered or dynamically scheduled plans) are packed best by ONE
+  // launch -- chunk boundaries would cut the order into pieces and leave a tail per chunk -- and their copies are small
+  // next to their compute: up to kSingleShotBytes of input they go up in one piece.
+  constexpr size_t kSingleShotBytes = 64u << 20;
+  const bool single_shot = (plan.order || plan.dynamic) &&
+                           static_cast<size_t>(n_episodes) * (BGR_N_PARAMS * sizeof(float) + BGR_N_STATE * sizeof(double)) <=
+                               kSingleShotBytes;
+  const std::vector<long long> chunks = single_shot ? std::vector<long long>{static_cast<long long>(n_episodes)}
+                                                    : host_chunks(n_episodes, plan.dynamic ? 4 * plan.wave_dyn : plan.wave);
   const int grid_total = static_cast<int>((n_episodes + kRolloutThreads - 1) / kRolloutThreads);
   BGR_TRY(ensure_chunk_events(chunks.size()));
   Slot* sl = nullptr;
@@ -1477,8 +1485,17 @@ struct bgr_mpc_bank {
   // device arena of the HOST entry point (states, outputs, evaluator scratch of one call), grown on demand: a call
   // through the handle makes no allocation at all; host calls on one handle are serialised by `call_mu`
   std::mutex call_mu;
-  unsigned char* arena = nullptr;
-  size_t arena_bytes = 0;
+  // Two arenas: a synchronous call uses slot 0; asynchronous calls (bgr_mpc_eval_bank_host_async) alternate, so that the
+  // upload of call i + 1 can run under the kernels of call i.  A slot remembers the stream of its last call and waits
+  // for it when it comes back on another stream.
+  struct Arena {
+    unsigned char* mem = nullptr;
+    size_t bytes = 0;
+    cudaStream_t last = nullptr;
+    bool used = false;
+  };
+  Arena arenas[2];
+  unsigned next_async = 0;
 };
 
 namespace {
@@ -1578,7 +1595,7 @@ int mpc_eval_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_
 int mpc_eval_host_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes, const double* h_state,
                        const int32_t* h_ref_start, const int32_t* h_ref_len, const float* h_bank, int32_t n_candidates,
                        bgr_mpc_bank* bank_handle, float* h_best_u, float* h_best_cost, int32_t* h_best_idx,
-                       float* h_costs, cudaStream_t stream, const char* who) {
+                       float* h_costs, cudaStream_t stream, const char* who, bool synchronous = true) {
   BGR_TRY(validate_mpc(track, cfg, n_episodes, n_candidates, who));
   if (n_episodes == 0) return BGR_OK;
   if (h_state == nullptr || h_ref_start == nullptr || (h_bank == nullptr && bank_handle == nullptr)) {
@@ -1610,15 +1627,19 @@ int mpc_eval_host_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64
                  o_u = o_len + up(E * sizeof(int32_t)), o_cost = o_u + up(E * 2 * sizeof(float)),
                  o_idx = o_cost + up(E * sizeof(float)), o_eval = o_idx + up(E * sizeof(int32_t)),
                  total = o_eval + up(E * sizeof(unsigned long long)) + up(mpc_epi_bytes(n_episodes)) + 256;
-    if (bank_handle->arena_bytes < total) {
-      BGR_CUDA(cudaStreamSynchronize(stream));
-      cudaFree(bank_handle->arena);
-      bank_handle->arena = nullptr;
-      bank_handle->arena_bytes = 0;
-      BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&bank_handle->arena), total + total / 4));
-      bank_handle->arena_bytes = total + total / 4;
+    bgr_mpc_bank::Arena& ar = bank_handle->arenas[synchronous ? 0 : 1 & bank_handle->next_async++];
+    if (ar.used && ar.last != stream) BGR_CUDA(cudaStreamSynchronize(ar.last));   // the slot's previous call, elsewhere
+    if (ar.bytes < total) {
+      if (ar.used) BGR_CUDA(cudaStreamSynchronize(ar.last));
+      cudaFree(ar.mem);
+      ar.mem = nullptr;
+      ar.bytes = 0;
+      BGR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ar.mem), total + total / 4));
+      ar.bytes = total + total / 4;
     }
-    unsigned char* a = bank_handle->arena;
+    ar.last = stream;
+    ar.used = true;
+    unsigned char* a = ar.mem;
     d_state = reinterpret_cast<double*>(a + o_state);
     d_start = reinterpret_cast<int32_t*>(a + o_start);
     if (h_ref_len != nullptr) d_len = reinterpret_cast<int32_t*>(a + o_len);
@@ -1653,7 +1674,7 @@ int mpc_eval_host_core(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64
     BGR_CUDA(cudaMemcpyAsync(h_best_idx, d_idx, E * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   if (h_costs != nullptr)
     BGR_CUDA(cudaMemcpyAsync(h_costs, d_costs, E * K * sizeof(float), cudaMemcpyDeviceToHost, stream));
-  BGR_CUDA(cudaStreamSynchronize(stream));
+  if (synchronous) BGR_CUDA(cudaStreamSynchronize(stream));
   return BGR_OK;
 }
 
@@ -1731,7 +1752,10 @@ extern "C" void bgr_mpc_bank_destroy(bgr_mpc_bank_t* bank) {
   if (bank == nullptr) return;
   DeviceScope dev(bank->device);
   cudaFree(bank->d_bank);
-  cudaFree(bank->arena);
+  for (auto& ar : bank->arenas) {
+    if (ar.used) cudaStreamSynchronize(ar.last);
+    cudaFree(ar.mem);
+  }
   for (auto& st : bank->stats) cudaFree(st.d_cand);
   delete bank;
 }
@@ -1752,6 +1776,16 @@ extern "C" int bgr_mpc_eval_bank_host(const bgr_track_t* track, const bgr_mpc_cf
   BGR_TRY(check_bank_handle(track, cfg, bank, "bgr_mpc_eval_bank_host"));
   return mpc_eval_host_core(track, cfg, n_episodes, h_state, h_ref_start, h_ref_len, nullptr, bank->K, bank, h_best_u,
                             h_best_cost, h_best_idx, h_costs, static_cast<cudaStream_t>(stream), "bgr_mpc_eval_bank_host");
+}
+
+extern "C" int bgr_mpc_eval_bank_host_async(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                                            const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
+                                            bgr_mpc_bank_t* bank, float* h_best_u, float* h_best_cost,
+                                            int32_t* h_best_idx, void* stream) {
+  BGR_TRY(check_bank_handle(track, cfg, bank, "bgr_mpc_eval_bank_host_async"));
+  return mpc_eval_host_core(track, cfg, n_episodes, h_state, h_ref_start, h_ref_len, nullptr, bank->K, bank, h_best_u,
+                            h_best_cost, h_best_idx, nullptr, static_cast<cudaStream_t>(stream),
+                            "bgr_mpc_eval_bank_host_async", false);
 }
 
 // ================================================================================================

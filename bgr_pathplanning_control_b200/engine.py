@@ -8,6 +8,7 @@ these functions raise.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -297,6 +298,26 @@ _group_streams = {}
 _group_pool = None
 
 
+_worker_local = threading.local()
+
+
+def _group_worker(track, config, params, init_state, aggregate, out):
+    """One group of a host-buffer ``rollout_groups`` call, on a pool thread.  The call is ordered on a stream that
+    belongs to the thread: on the legacy default stream (``stream = NULL``) the completion wait of one thread's call
+    would sit in front of the next thread's first upload, and the groups would run one after the other."""
+    lib = abi.load()
+    streams = getattr(_worker_local, "streams", None)
+    if streams is None:
+        streams = _worker_local.streams = {}
+    st = streams.get(track.device)
+    if st is None:
+        st = C.c_void_p()
+        abi.check(lib.bgr_stream_create(int(track.device), C.byref(st)))
+        streams[track.device] = st
+    cfg = config.to_struct() if isinstance(config, RolloutConfig) else config
+    return _rollout_numpy(lib, track, cfg, params, init_state, False, aggregate, out, stream=st)
+
+
 def _host_group_pool(n):
     global _group_pool
     if _group_pool is None or _group_pool._max_workers < n:
@@ -320,8 +341,8 @@ def rollout_groups(track, groups, *, aggregate=False, outs=None, order=None):
         # worker threads PERSIST across calls: the library keeps its host-buffer pipeline (streams, device buffer ring)
         # per host thread, and a fresh thread would have to build it again
         pool = _host_group_pool(len(groups))
-        futs = {g: pool.submit(rollout, track, groups[g][0], groups[g][1], groups[g][2], aggregate=aggregate,
-                               out=None if outs is None else outs[g]) for g in seq}
+        futs = {g: pool.submit(_group_worker, track, groups[g][0], groups[g][1], groups[g][2], aggregate,
+                               None if outs is None else outs[g]) for g in seq}
         return [futs[g].result() for g in range(len(groups))]
     torch = _torch()
     dev = torch.device("cuda", track.device)
@@ -360,7 +381,7 @@ def release_group_streams():
     _group_streams.clear()
 
 
-def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out=None):
+def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out=None, stream=None):
     params = _np(params, np.float32)
     E = params.shape[0]
     params = _np(params, np.float32, (E, abi.N_PARAMS))
@@ -376,7 +397,7 @@ def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out=Non
     tr = np.zeros((E, cfg.max_steps, abi.N_TRAJ)) if traj else None
     agg = np.empty(abi.N_AGG) if aggregate else None
     abi.check(lib.bgr_rollout_host(track.handle, C.byref(cfg), E, _ptr(params), _ptr(init_state), _ptr(metrics),
-                                   _ptr(status), _ptr(tr), _ptr(agg), None))
+                                   _ptr(status), _ptr(tr), _ptr(agg), stream))
     return RolloutResult(metrics, status, tr, agg, None)
 
 
@@ -697,6 +718,59 @@ def _mpc_evaluate_bank(lib, track, cfg, state, ref_start, bank, ref_len, return_
                                     bank.handle, _ptr(u), _ptr(cost), _ptr(idx), _ptr(costs), stream))
     ms = last_kernel_ms() if time_kernel and E > 0 else None
     return MpcResult(u, cost, idx, costs, ms)
+
+
+class PendingMpc:
+    """A host-buffer MPC evaluation that has been queued but not waited for (``mpc_evaluate_async``)."""
+
+    def __init__(self, lib, stream, result, keep):
+        self._lib, self._stream, self._result, self._keep, self._done = lib, stream, result, keep, False
+
+    def wait(self):
+        if not self._done:
+            abi.check(self._lib.bgr_stream_synchronize(self._stream))
+            self._done = True
+            self._keep = None
+        return self._result
+
+
+_mpc_async_next = {}
+
+
+def mpc_evaluate_async(track, config, state, ref_start, bank, ref_len=None, *, out=None):
+    """``mpc_evaluate`` for HOST (numpy, ideally pinned) states and a resident ``MpcBank`` without the final
+    synchronise (``bgr_mpc_eval_bank_host_async``): returns a ``PendingMpc``.  Queue batch i + 1 before ``wait()``-ing
+    batch i and its upload runs under batch i's kernels (consecutive calls alternate between two streams and two device
+    arenas).  The arrays must not be touched until ``wait()`` returns; give each of the (at most two) batches in flight
+    its own ``out``."""
+    lib = abi.load()
+    if not isinstance(bank, MpcBank):
+        raise TypeError("mpc_evaluate_async needs a resident MpcBank")
+    cfg = config.to_struct() if isinstance(config, MpcConfig) else config
+    state = _np(state, np.float64)
+    E = state.shape[0]
+    state = _np(state, np.float64, (E, 4))
+    ref_start = _np(ref_start, np.int32, (E,))
+    ref_len = None if ref_len is None else _np(ref_len, np.int32, (E,))
+    if out is not None:
+        u, cost, idx = out.best_u, out.best_cost, out.best_idx
+        if (u.dtype != np.float32 or u.shape != (E, 2) or cost.dtype != np.float32 or cost.shape != (E,)
+                or idx.dtype != np.int32 or idx.shape != (E,)):
+            raise ValueError("out must hold (E, 2) float32, (E,) float32 and (E,) int32 arrays")
+    else:
+        u, cost, idx = np.empty((E, 2), np.float32), np.empty(E, np.float32), np.empty(E, np.int32)
+    # two of the library-side streams of rollout_async, alternating
+    pool = _async_streams.setdefault(track.device, [])
+    while len(pool) < 2:
+        h = C.c_void_p()
+        abi.check(lib.bgr_stream_create(int(track.device), C.byref(h)))
+        pool.append(h)
+    i = _mpc_async_next.get(track.device, 0)
+    _mpc_async_next[track.device] = i ^ 1
+    stream = pool[i]
+    abi.check(lib.bgr_mpc_eval_bank_host_async(track.handle, C.byref(cfg), E, _ptr(state), _ptr(ref_start), _ptr(ref_len),
+                                               bank.handle, _ptr(u), _ptr(cost), _ptr(idx), stream))
+    return PendingMpc(lib, stream, MpcResult(u, cost, idx, None), (state, ref_start, ref_len, bank))
 
 
 def identify_dynamics(traj, rows=None):

@@ -395,6 +395,17 @@ int bgr_mpc_eval_bank_host(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, i
                            bgr_mpc_bank_t* bank, float* h_best_u, float* h_best_cost, int32_t* h_best_idx,
                            float* h_costs, void* stream);
 
+/* The same without the final synchronise: the uploads, kernels and downloads are queued on `stream` and the call
+ * returns; the result arrays are valid after the caller has synchronised `stream` (bgr_stream_synchronize), and neither
+ * they nor the inputs may be touched before.  Consecutive calls on one handle alternate between two device arenas, so
+ * issuing call i + 1 on a SECOND stream before waiting for call i lets its upload run under call i's kernels -- a
+ * streaming caller with two sets of pinned buffers then pays the kernels, not kernels + copies.  At most two calls in
+ * flight per handle (a third waits for the arena it needs). */
+int bgr_mpc_eval_bank_host_async(const bgr_track_t* track, const bgr_mpc_cfg_t* cfg, int64_t n_episodes,
+                                 const double* h_state, const int32_t* h_ref_start, const int32_t* h_ref_len,
+                                 bgr_mpc_bank_t* bank, float* h_best_u, float* h_best_cost, int32_t* h_best_idx,
+                                 void* stream);
+
 /* ---- batched system identification: identify_dynamics (old/test_runs_system_id.py:84-111) for every episode of a
  *      trajectory dump: least squares x_{k+1} = A x_k + B u_k + c over the logged rows, x = [x, y, yaw, v, yaw_rate,
  *      beta], u = [accel, steering] (LinearRegression with an intercept on hstack([X, U]) -> Y).

@@ -253,3 +253,36 @@ def test_resident_bank_handle_equals_the_array_path(cuda_device):
     with pytest.raises(RuntimeError):
         bgr.mpc_evaluate(track, bgr.MpcConfig(horizon=H, dt=0.05), states, ref_start, resident)
 
+
+
+def test_async_bank_evaluation_pipelines_and_matches(cuda_device):
+    """bgr_mpc_eval_bank_host_async: batches queued back to back on alternating streams / arenas, each with its own pinned
+    buffers; every batch must equal the synchronous call, also when a third batch comes back to the first arena and
+    when a synchronous call is mixed in."""
+    import torch
+    ta = bgr.tracks.stadium_oval(1024)
+    track = bgr.Track.from_arrays(ta)
+    cfg = bgr.MpcConfig(horizon=30, dt=0.05)
+    K = 512
+    bank = bgr.MpcBank(bgr.candidate_bank(K, 30, seed=3))
+    batches = []
+    for b, E in enumerate((4096, 1000, 4096, 7, 2048)):
+        st, rs = bgr.sweeps.mpc_states(ta, E, start=1000 * b)
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()      # noqa: E731
+        out = bgr.MpcResult(pin(np.empty((E, 2), np.float32)), pin(np.empty(E, np.float32)), pin(np.empty(E, np.int32)))
+        batches.append((pin(st), pin(rs), out))
+    want = [bgr.mpc_evaluate(track, cfg, st, rs, bank) for st, rs, _ in batches]
+    pend = [bgr.mpc_evaluate_async(track, cfg, st, rs, bank, out=out) for st, rs, out in batches[:2]]
+    for i, (st, rs, out) in enumerate(batches[2:], 2):
+        got = pend[i - 2].wait()
+        assert got is pend[i - 2].wait()
+        pend.append(bgr.mpc_evaluate_async(track, cfg, st, rs, bank, out=out))
+        if i == 3:                                                     # a synchronous call in between shares arena 0
+            mid = bgr.mpc_evaluate(track, cfg, batches[0][0], batches[0][1], bank)
+            assert np.array_equal(mid.best_idx, want[0].best_idx)
+    for p, w in zip(pend, want):
+        r = p.wait()
+        assert np.array_equal(r.best_idx, w.best_idx) and np.array_equal(r.best_u, w.best_u)
+        assert np.array_equal(r.best_cost, w.best_cost)
+    with pytest.raises(TypeError):
+        bgr.mpc_evaluate_async(track, cfg, batches[0][0], batches[0][1], bank.array)

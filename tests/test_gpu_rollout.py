@@ -748,6 +748,18 @@ def test_launch_order_by_speed_is_bit_identical(cuda_device, steer, accel, model
     assert np.array_equal(out[True][2], out[False][2], equal_nan=True)
     steps = out[True][1][:, abi.S_STEPS]
     assert steps.max() > 1.2 * np.median(steps)     # the lengths do differ: the order matters for the schedule
+    if clean:
+        # host buffers beyond the single-upload size (64 MiB of input): the call is cut into wave-sized chunks, each
+        # ordered on its own -- still the same rows
+        Eb = 620_000
+        pb = bgr.sweeps.monte_carlo_params(Eb, start=5)
+        ib = np.repeat(init[:1], Eb, axis=0)
+        cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=1)
+        hb = bgr.rollout(track, cfg, pb, ib)
+        db = bgr.rollout(track, bgr.RolloutConfig(**{**cfg.__dict__, "keep_order": True}),
+                         torch.from_numpy(pb).to(cuda_device), torch.from_numpy(ib).to(cuda_device))
+        assert np.array_equal(hb.metrics, db.metrics.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(hb.status, db.status.cpu().numpy())
 
 
 def test_launch_order_small_batches_and_closed_tracks_keep_row_order(cuda_device):
