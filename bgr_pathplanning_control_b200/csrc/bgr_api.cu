@@ -910,6 +910,10 @@ int launch_range(const Plan& plan, long long id_offset, long long count, const f
     BGR_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int32_t), stream));
     A.queue = d_queue;
     grid = static_cast<int>(std::min<long long>(grid, plan.wave_dyn / kRolloutThreads));
+    {   // (tuning: BGR_DYN_GRID_PCT=<percent of one wave>)
+      static const int pct = [] { const char* e = std::getenv("BGR_DYN_GRID_PCT"); return e ? std::atoi(e) : 100; }();
+      if (pct > 0 && pct != 100) grid = std::max(1, static_cast<int>(static_cast<long long>(grid) * pct / 100));
+    }
   }
   cudaError_t err = plan.fn(A, grid, plan.smem, plan.smem_optin, stream, nullptr);
   if (err == cudaSuccess) count_launch();

@@ -32,5 +32,6 @@ cap replan rollout_kernel 1 --workload pp_replan
 # config 5: the pure-pursuit kind is the launch that fills the GPU.  Kinds launch in the order stanley+lqg, stanley+pid,
 # pp, all instantiations of rollout_kernel_f32 (ncu matches base names): launch #6 is the pp kind of the first timed step
 cap mc rollout_kernel_f32 5 --workload skidpad_mc
+cap mc_stlqg rollout_kernel_f32 3 --workload skidpad_mc     # launch #4: stanley+lqg+dynamic on the dynamic queue
 cap mpc mpc_factored_kernel 1 --workload mpc
 ls -la gpurun_out | head -60

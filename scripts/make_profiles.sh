@@ -47,6 +47,10 @@ PY
 }
 summarise prof_replan pp_replan bgr_rollout_inst_f32_full _ZN3bgr18rollout_kernel_f32ILi0ELi0ELi0ELb1ELb1ELb0EEEvNS_11RolloutArgsE "$(units gpurun_out/plain_replan.log 1)"
 summarise prof_mc config5_pp bgr_rollout_inst_f32_full _ZN3bgr18rollout_kernel_f32ILi0ELi0ELi0ELb1ELb1ELb0EEEvNS_11RolloutArgsE 0
+summarise prof_mc_stlqg config5_stanley_lqg_queue bgr_rollout_inst_f32_full _ZN3bgr18rollout_kernel_f32ILi1ELi1ELi1ELb1ELb1ELb1EEEvNS_11RolloutArgsE 0
+for r in mc:config5_pp mc_stlqg:config5_stanley_lqg_queue; do
+  [ -f "gpurun_out/prof_${r%%:*}.ncu-rep" ] && python scripts/ncu_regions.py "gpurun_out/prof_${r%%:*}.ncu-rep" > "$out/regions_${r##*:}.txt"
+done
 if [ -f gpurun_out/prof_mpc.ncu-rep ]; then
   ncu -i gpurun_out/prof_mpc.ncu-rep --page raw --csv > "$tmp/mpc_raw.csv" 2> /dev/null
   python scripts/ncu_summary.py "$tmp/mpc_raw.csv" > "$out/ncu_full_mpc_factored.json"
