@@ -517,6 +517,7 @@ def run_rollout_workload(ctx, workload, E, S, steps, warmup, *, strong_total=Non
         "frac": achieved_tflops / fp32_tflops, "traffic": ncu.get("dram_bytes_per_launch"),
         "peak_source": "bgr_fp32_peak_probe (FFMA chains, measured in this run); MEASURED_PEAKS.json has no fp32 row",
         "flops_per_sim_step": flops_step, "kernel_ms_avg": k_ms, "kernel_ms_last": kernel_ms_last,
+        "step_ms": [round(x, 3) for x in kernel_ms],
         "sim_steps_per_launch": steps_per_launch,
         # what ncu measured for THIS library build (profiles/<dir>/, matched by build id): the kernel is bound by
         # INSTRUCTION ISSUE, not by DRAM or tensor throughput
