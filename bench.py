@@ -579,7 +579,7 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
             noise.update(sigma_xy=0.0, sigma_yaw=0.0, sigma_v=0.0)
     jobs, dynamic = [], []
     for g, (steer, accel, model) in enumerate(kinds):
-        lo = (rank * len(kinds) + g) * per
+        lo = ((rank + int(os.environ.get("BGR_MC_ROW_RANK", "0"))) * len(kinds) + g) * per   # (diagnostic: another rank's rows)
         # diagnostics: BGR_MC_SPLIT=<steps> (two-phase run), BGR_MC_DYNAMIC=1 (dynamic schedule), both for the kinds
         # listed in BGR_MC_KINDS (default: all), e.g. BGR_MC_KINDS=1,2 = the two Stanley kinds
         on = str(g) in os.environ.get("BGR_MC_KINDS", "0,1,2").split(",")

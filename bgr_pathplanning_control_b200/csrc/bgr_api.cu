@@ -384,10 +384,12 @@ extern "C" void bgr_track_destroy(bgr_track_t* t) {
   cudaFree(t->rival_range);
   cudaFree(t->rival_list);
   cudaFree(t->twin);
+  cudaFree(t->scan_blk);
   cudaFree(t->cone_range);
   cudaFree(t->cone_near);
   cudaFree(t->cone_list);
   cudaFree(t->cones);
+  cudaFree(t->cones_f);
   for (auto& k : t->kf_tables) {
     cudaFree(k.d_gain);
     cudaFree(k.d_gain_f);
@@ -510,6 +512,24 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     g = std::isfinite(g) ? std::max(0.0, g * (1.0 - 1e-4) - 1e-4) : 1e18;
     guard2[j] = static_cast<float>(std::min(g * g, 1e30));
   }
+  // Bounding circles of blocks of 32 consecutive waypoints, of the ROUNDED waypoints the fp32 kernels read: centre =
+  // the block's mean (as floats), radius = the largest distance of a member from that float centre, rounded up.  The
+  // exact scan evaluates a block only if |p - centre| - radius does not exceed the distance already in hand.
+  std::vector<float4> scan_blk((n + 31) / 32);
+  for (int b = 0; b < static_cast<int>(scan_blk.size()); ++b) {
+    const int lo = 32 * b, hi = std::min(n, lo + 32);
+    double mx = 0.0, my = 0.0;
+    for (int i = lo; i < hi; ++i) {
+      mx += static_cast<double>(static_cast<float>(t->x[i]));
+      my += static_cast<double>(static_cast<float>(t->y[i]));
+    }
+    const float cx = static_cast<float>(mx / (hi - lo)), cy = static_cast<float>(my / (hi - lo));
+    double r = 0.0;
+    for (int i = lo; i < hi; ++i)
+      r = std::max(r, std::hypot(static_cast<double>(static_cast<float>(t->x[i])) - static_cast<double>(cx),
+                                 static_cast<double>(static_cast<float>(t->y[i])) - static_cast<double>(cy)));
+    scan_blk[b] = make_float4(cx, cy, std::nextafterf(static_cast<float>(r * (1.0 + 1e-6) + 1e-6), INFINITY), 0.0f);
+  }
 
   // rival lists: (first, count) per waypoint; count < 0 = no usable list (exact scan instead)
   for (int j = 0; j < n; ++j) {
@@ -554,6 +574,7 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
   cudaGetDevice(&prev);
   rc = check_cuda(cudaSetDevice(device), "cudaSetDevice");
   if (rc == BGR_OK) rc = upload(&t->xy_f, xy_f);
+  if (rc == BGR_OK) rc = upload(&t->scan_blk, scan_blk);
   if (rc == BGR_OK) rc = upload(&t->attr_f, attr_f);
   if (rc == BGR_OK) rc = upload(&t->xy_d, xy_d);
   if (rc == BGR_OK) rc = upload(&t->attr_d, attr_d);
@@ -566,6 +587,12 @@ extern "C" int bgr_track_create(const bgr_track_desc_t* desc, int device, bgr_tr
     if (rc == BGR_OK) rc = upload(&t->cone_near, cone_near);
     if (rc == BGR_OK) rc = upload(&t->cone_list, cone_list);
     if (rc == BGR_OK) rc = upload(&t->cones, cones);
+    if (rc == BGR_OK) {
+      std::vector<float2> cones_f(t->n_cones);
+      for (int c = 0; c < t->n_cones; ++c)
+        cones_f[c] = make_float2(static_cast<float>(cones[c].x), static_cast<float>(cones[c].y));
+      rc = upload(&t->cones_f, cones_f);
+    }
   }
   cudaSetDevice(prev);
   if (rc != BGR_OK) {

@@ -56,10 +56,13 @@ struct TrackView {
   const int2* rival_list;     // (waypoint, bits of its squared reach-in distance), ascending per list
   const int2* twin;           // [n] (twin waypoint t or -1, bits of the squared twin guard): inside it the exact argmin is
                               // the best of the descent's answer and t - 1, t, t + 1 (bgr_api.cu: compute_guards)
+  const float4* scan_blk;     // [ceil(n / 32)] (centre x, centre y, radius, -) of 32 consecutive waypoints: the exact
+                              // scan of the fp32 kernels skips every block that provably holds nothing within reach
   const int32_t* cone_range;  // [n] (first << 10) | count  into cone_list
   const float* cone_near;     // [n] distance from waypoint j to its closest listed cone, rounded down
   const int32_t* cone_list;
   const double2* cones;       // [n_cones]
+  const float2* cones_f;      // [n_cones] rounded copy: the fp32 kernels' cheap distance pre-test in front of the exact one
   int32_t n;
   int32_t n_pad;
   int32_t closed;

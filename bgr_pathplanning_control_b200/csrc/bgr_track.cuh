@@ -19,10 +19,12 @@ struct bgr_track {
   int2* rival_range = nullptr;     // per waypoint (first, count) into rival_list; count < 0: no usable list
   int2* rival_list = nullptr;      // (waypoint, float bits of the squared distance from w_j at which it can first win)
   int2* twin = nullptr;            // per waypoint (twin waypoint t or -1, float bits of the squared twin guard)
+  float4* scan_blk = nullptr;      // bounding circles of blocks of 32 waypoints (exact-scan pruning)
   int32_t* cone_range = nullptr;
   float* cone_near = nullptr;   // [n] distance from waypoint j to its closest listed cone (rounded down)
   int32_t* cone_list = nullptr;
   double2* cones = nullptr;
+  float2* cones_f = nullptr;
   // LQG Kalman gain sequences, uploaded on first use per (dt, length); freed with the handle
   struct KfTable {
     double dt = 0;
@@ -43,8 +45,8 @@ struct bgr_track {
   bgr::TrackView view() const {
     bgr::TrackView v;
     v.xy_f = xy_f; v.attr_f = attr_f; v.xy_d = xy_d; v.attr_d = attr_d; v.guard2 = guard2;
-    v.rival_range = rival_range; v.rival_list = rival_list; v.twin = twin;
-    v.cone_range = cone_range; v.cone_near = cone_near; v.cone_list = cone_list; v.cones = cones;
+    v.rival_range = rival_range; v.rival_list = rival_list; v.twin = twin; v.scan_blk = scan_blk;
+    v.cone_range = cone_range; v.cone_near = cone_near; v.cone_list = cone_list; v.cones = cones; v.cones_f = cones_f;
     v.n = n; v.n_pad = n_pad; v.closed = closed; v.n_cones = n_cones;
     v.ds_max = static_cast<float>(ds_max);
     return v;

@@ -18,11 +18,13 @@ track = bgr.Track.from_arrays(ta, device=0, cone_reach=4.0)
 print("env BGR_ATTR_IN_SMEM =", repr(os.environ.get("BGR_ATTR_IN_SMEM")), "track info", track.info())
 noise = dict(sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1, sigma_cone=0.05, noise_seed=20261022, hit_radius=0.5)
 kinds = [("pure_pursuit", "pid", "kinematic"), ("stanley", "pid", "kinematic"), ("stanley", "lqg", "dynamic")]
-for g, (steer, accel, model) in enumerate(kinds):
+rr = int(os.environ.get("BGR_MC_ROW_RANK", "0"))
+for g0, (steer, accel, model) in enumerate(kinds):
+    g = g0 + 3 * rr
     for label, extra in (("noise+cones", noise), ("noise only", {**noise, "hit_radius": 0.0}),
                          ("clean (lean build)", {})):
         cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=1500, laps=1, episode_id_base=g * per,
-                                dynamic_schedule=os.environ.get("BGR_MC_DYNAMIC") == "1", **extra)
+                                dynamic_schedule=os.environ.get("BGR_MC_DYNAMIC", "1" if steer == "stanley" else "0") == "1", **extra)
         init = bgr.initial_states(ta, per, index=0, v0=5.0 if model == "dynamic" else 0.0)
         init[:, abi.YAW] = 0.0
         p = torch.from_numpy(bgr.sweeps.monte_carlo_params(per, start=g * per)).to(dev)

@@ -84,3 +84,50 @@ def test_logged_nearest_index_is_the_global_argmin(cuda_device, kind, n, steer):
     print(f"{kind} n={n} {steer}: {checked} steps checked, {ties} inside the tie band, {far} with the car > 2.5 m "
           f"from every waypoint (exact warp scan), rivals {info['rival_total']} (max {info['rival_max']}), "
           f"fallbacks per episode {res.status[:, abi.S_FALLBACKS].mean():.1f}")
+
+
+@pytest.mark.parametrize("kind,n", [("blob", 777), ("lemniscate", 2050), ("double_lap", 901), ("hairpin", 450),
+                                    ("blob", 61), ("blob", 33), ("blob", 5)])
+def test_lost_cars_scan_exactly(cuda_device, kind, n):
+    """Cars that start 3 ... 400 m away from the track and mostly stay lost: every search is the exact scan, which
+    evaluates only the blocks of 32 waypoints whose bounding circle reaches inside the distance already in hand
+    (DESIGN.md section 4).  The logged index must still be the global argmin at every step, on tracks whose length is
+    not a multiple of the block size, with the car inside, outside and far away from the track's hull, for the true pose
+    (pure pursuit: error logging) and for noisy observed poses (Stanley: two searches per step)."""
+    rng = np.random.default_rng(hash((kind, n, "lost")) % (1 << 31))
+    cx, cy, closed = random_track(rng, kind, n)
+    track = bgr.Track(cx, cy, None, closed=closed)
+    E, S = 128, 120
+    params = bgr.default_params(E)
+    params[:, abi.P_TARGET_SPEED] = rng.uniform(3.0, 12.0, E)
+    ang, rad = rng.uniform(0, 2 * np.pi, E), np.exp(rng.uniform(np.log(3.0), np.log(400.0), E))
+    j0 = rng.integers(0, n, E)
+    init = np.zeros((E, 6))
+    init[:, 0] = cx[j0] + rad * np.cos(ang)
+    init[:, 1] = cy[j0] + rad * np.sin(ang)
+    init[:, 2] = rng.uniform(-np.pi, np.pi, E)
+    init[:, 3] = rng.uniform(0.0, 15.0, E)
+    scans = 0
+    for steer, noise in (("pure_pursuit", {}), ("stanley", dict(sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1, noise_seed=5))):
+        cfg = bgr.RolloutConfig(steer=steer, accel="pid", model="kinematic", max_steps=S, laps=2, **noise)
+        res = bgr.rollout(track, cfg, params, init, traj=True)
+        for e in range(E):
+            k = int(res.status[e, abi.S_STEPS])
+            tr = res.traj[e, :k]
+            d = np.hypot(cx[None, :] - tr[:, abi.T_X, None], cy[None, :] - tr[:, abi.T_Y, None])
+            want = np.argmin(d, axis=1)
+            got = tr[:, abi.T_NEAREST_IND].astype(np.int64)
+            if n > 1:
+                part = np.partition(d, 1, axis=1)
+                margin = part[:, 1] - part[:, 0]
+            else:
+                margin = np.full(k, np.inf)
+            bad = got != want
+            # the fp32 offsets of a car hundreds of metres out carry ulp(|p|) / 2 each: the band grows with the distance
+            band = TIE + 1e-6 * d.min(axis=1)
+            assert not np.any(bad & (margin >= band)), (kind, n, steer, e, int(np.nonzero(bad & (margin >= band))[0][0]))
+            if np.any(bad):
+                kk = np.nonzero(bad)[0]
+                assert np.all(d[kk, got[kk]] - d[kk, want[kk]] < band[kk])
+        scans += int(res.status[:, abi.S_FALLBACKS].sum())
+    assert scans > E * S // 2          # the exact scan did run for most of these steps
