@@ -20,7 +20,8 @@ from .vehicle_config import Vehicle_config, conf               # noqa: F401
 from .engine import (Track, RolloutConfig, RolloutResult, MpcConfig, MpcResult, rollout, rollout_groups, mpc_evaluate,   # noqa: F401
                      default_params, initial_states, candidate_bank, lqg_design, lqg_covariance, fp32_peak_probe,
                      last_kernel_ms, launch_count, identify_dynamics, rollout_async, PendingRollout, build_id,
-                     release_group_streams, MpcBank, fp64_peak_probe, mpc_evaluate_async, PendingMpc)
+                     release_group_streams, MpcBank, fp64_peak_probe, mpc_evaluate_async, PendingMpc,
+                     rollout_groups_async, PendingGroups)
 from .controllers import (PurePursuitController, StanleyController, ShadowedStanleyController, AccelerationPIDController,            # noqa: F401
                           LQGAccelerationController, MPCController, get_steering_controller,
                           normalize_angle, find_target_point, compute_control_commands)

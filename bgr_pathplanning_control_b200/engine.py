@@ -401,20 +401,25 @@ def _rollout_numpy(lib, track, cfg, params, init_state, traj, aggregate, out=Non
     return RolloutResult(metrics, status, tr, agg, None)
 
 
-_async_streams = {}      # device -> [cudaStream_t, ...]: each in-flight host-buffer rollout completes on its own stream
-_async_next = {}
+_async_local = threading.local()   # per host thread, like the library's pipeline: device -> [cudaStream_t, ...]
 _ASYNC_DEPTH = 4
 
 
 def _async_stream(lib, device):
-    pool = _async_streams.setdefault(device, [])
+    """The completion stream of the calling thread's next in-flight host-buffer rollout (round robin over
+    ``_ASYNC_DEPTH`` streams per thread and device: each in-flight call completes on its own stream)."""
+    pools = getattr(_async_local, "pools", None)
+    if pools is None:
+        pools = _async_local.pools = {}
+        _async_local.next = {}
+    pool = pools.setdefault(device, [])
     if len(pool) < _ASYNC_DEPTH:
         h = C.c_void_p()
         abi.check(lib.bgr_stream_create(int(device), C.byref(h)))
         pool.append(h)
         return pool[-1]
-    i = _async_next.get(device, 0)
-    _async_next[device] = (i + 1) % _ASYNC_DEPTH
+    i = _async_local.next.get(device, 0)
+    _async_local.next[device] = (i + 1) % _ASYNC_DEPTH
     return pool[i]
 
 
@@ -460,6 +465,44 @@ def rollout_async(track, config, params, init_state, *, aggregate=False, out=Non
     abi.check(lib.bgr_rollout_host_async(track.handle, C.byref(cfg), E, _ptr(params), _ptr(init_state), _ptr(metrics),
                                          _ptr(status), _ptr(agg), stream))
     return PendingRollout(lib, stream, RolloutResult(metrics, status, None, agg, None), (params, init_state, cfg, track))
+
+
+_group_lanes = []      # one single-thread executor per group index: group g always runs on ITS thread (and pipeline)
+
+
+class PendingGroups:
+    """The groups of one ``rollout_groups_async`` call.  ``wait()`` returns one ``RolloutResult`` per group (in the
+    order the groups were given) once every group's result arrays are filled."""
+
+    def __init__(self, futures):
+        self._futures, self._results = futures, None
+
+    def wait(self):
+        if self._results is None:
+            self._results = [f.result().wait() for f in self._futures]
+            self._futures = None
+        return self._results
+
+
+def rollout_groups_async(track, groups, *, aggregate=False, outs=None, order=None):
+    """``rollout_groups`` for HOST buffers without the final synchronise: every group is QUEUED
+    (``bgr_rollout_host_async``) from a host thread of its own -- group g always from the same thread, so it always
+    meets the same copy / compute pipeline and device buffer ring inside the library -- and a ``PendingGroups`` is
+    returned.  Queue batch i + 1 before ``wait()``-ing batch i: a Monte Carlo batch's uploads then run under the
+    previous batch's kernels and its downloads under the next batch's, and the few long episodes at the end of one
+    batch's heavy-tailed groups no longer hold the machine alone.  Same rules as ``rollout_async``: do not touch the
+    arrays of a batch before its ``wait()`` returns, give every in-flight batch its own ``outs``, at most 3 batches in
+    flight (the library's ring of device buffer slots per host thread)."""
+    from concurrent.futures import ThreadPoolExecutor
+    while len(_group_lanes) < len(groups):
+        _group_lanes.append(ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"bgr-lane{len(_group_lanes)}"))
+    seq = list(order) if order is not None else list(range(len(groups)))
+    futs = {}
+    for g in seq:
+        cfg, params, init = groups[g]
+        futs[g] = _group_lanes[g].submit(rollout_async, track, cfg, params, init, aggregate=aggregate,
+                                         out=None if outs is None else outs[g])
+    return PendingGroups([futs[g] for g in range(len(groups))])
 
 
 def build_id():

@@ -13,6 +13,14 @@ fi
 #  loop of one round averaged 16.5 ms per step against 14.5 ms without -- bench.py's own samples are the record)
 timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench default rc=$?"; tail -1 gpurun_out/bench_default.log | cut -c1-300
 for w in pp_replan; do timeout 600 python bench.py --workload $w --no-cpu-baseline > gpurun_out/bench_$w.log 2>&1; echo "bench $w rc=$?"; tail -1 gpurun_out/bench_$w.log | cut -c1-200; done
+# config 5 on the rows other ranks of an 8-GPU run would get (the step time of a multi-GPU run is the slowest rank's:
+# which rows hold the long / lost episodes decides it)
+for r in ${MC_ROW_RANKS:-3 6}; do
+  BGR_MC_ROW_RANK=$r timeout 300 python bench.py --workload skidpad_mc --steps 5 --warmup 2 --no-cpu-baseline --no-secondary \
+    > gpurun_out/bench_mc_rows$r.log 2>&1; echo "bench skidpad_mc rows of rank $r rc=$?"; tail -1 gpurun_out/bench_mc_rows$r.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('   value %.4e  ms/step %.3f  e2e %.4e (sync %.4e)' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['one_call_at_a_time']['value']))"
+done
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "bench ref rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-200
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary"
 $CMD > gpurun_out/plain.log 2>&1 && \

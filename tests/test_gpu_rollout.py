@@ -610,6 +610,47 @@ def test_rollout_groups_from_host_buffers(cuda_device):
         assert np.array_equal(a.aggregate, b.aggregate)
 
 
+def test_streaming_rollout_groups_equal_the_synchronous_call(cuda_device):
+    """engine.rollout_groups_async: the Monte Carlo kinds of config 5 (speed-ordered pure pursuit, dynamically scheduled
+    noisy Stanley kinds) queued from one host thread per kind, three batches in flight with their own pinned result
+    buffers; every batch's rows equal the synchronous rollout_groups call bit for bit, whatever overlaps with what."""
+    import torch
+    ta = bgr.tracks.skidpad(2048)
+    track = bgr.Track.from_arrays(ta, cone_reach=4.0)
+    kinds = [("pure_pursuit", "pid", "kinematic"), ("stanley", "pid", "kinematic"), ("stanley", "lqg", "dynamic")]
+    E = 6000
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    batches = []
+    for b in range(3):
+        groups = []
+        for g, (steer, accel, model) in enumerate(kinds):
+            lo = (b * len(kinds) + g) * E
+            cfg = bgr.RolloutConfig(steer=steer, accel=accel, model=model, max_steps=700, laps=1, episode_id_base=lo,
+                                    dynamic_schedule=steer == "stanley", sigma_xy=0.05, sigma_yaw=0.01, sigma_v=0.1,
+                                    sigma_cone=0.05, noise_seed=11, hit_radius=0.5)
+            init = bgr.initial_states(ta, E + g, index=0, v0=5.0 if model == "dynamic" else 0.0)
+            init[:, abi.YAW] = 0.0
+            groups.append((cfg, pin(bgr.sweeps.monte_carlo_params(E + g, start=lo)), pin(init)))
+        outs = [bgr.RolloutResult(pin(np.empty((E + g, abi.N_METRICS), np.float32)),
+                                  pin(np.empty((E + g, abi.N_STATUS), np.int32)), None, pin(np.empty(abi.N_AGG)))
+                for g in range(len(kinds))]
+        batches.append((groups, outs))
+    for _ in range(2):          # second round: the lane threads' pipelines and buffer rings exist already
+        pend = [bgr.rollout_groups_async(track, groups, aggregate=True, outs=outs, order=[2, 1, 0])
+                for groups, outs in batches]
+        got = [p.wait() for p in pend]
+        assert pend[1].wait() is got[1]             # wait() is idempotent
+        for (groups, outs), res in zip(batches, got):
+            want = bgr.rollout_groups(track, groups, aggregate=True, order=[2, 1, 0])
+            for g, (w, r) in enumerate(zip(want, res)):
+                assert r.metrics is outs[g].metrics and r.aggregate is outs[g].aggregate
+                assert np.array_equal(w.status, r.status)
+                assert np.array_equal(w.metrics.view(np.int32), r.metrics.view(np.int32))
+                assert np.array_equal(w.aggregate, r.aggregate) and r.aggregate[abi.A_EPISODES] == E + g
+    # the batches differ (their own noise streams and parameter rows), so a mixed-up buffer would have shown
+    assert not np.array_equal(got[0][0].status, got[1][0].status)
+
+
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 def test_stepped_closed_loop_with_noise_equals_one_rollout(cuda_device, precision):
     """N calls of bgr_step_host that carry their controller row draw the SAME observation noise as one
