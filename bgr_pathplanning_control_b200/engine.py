@@ -777,6 +777,7 @@ class PendingMpc:
         return self._result
 
 
+_mpc_async_streams = {}      # device -> two completion streams, alternating (bgr_mpc_eval_bank_host_async)
 _mpc_async_next = {}
 
 
@@ -802,8 +803,7 @@ def mpc_evaluate_async(track, config, state, ref_start, bank, ref_len=None, *, o
             raise ValueError("out must hold (E, 2) float32, (E,) float32 and (E,) int32 arrays")
     else:
         u, cost, idx = np.empty((E, 2), np.float32), np.empty(E, np.float32), np.empty(E, np.int32)
-    # two of the library-side streams of rollout_async, alternating
-    pool = _async_streams.setdefault(track.device, [])
+    pool = _mpc_async_streams.setdefault(track.device, [])
     while len(pool) < 2:
         h = C.c_void_p()
         abi.check(lib.bgr_stream_create(int(track.device), C.byref(h)))
