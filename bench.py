@@ -472,8 +472,12 @@ def run_rollout_workload(ctx, workload, E, S, steps, warmup, *, strong_total=Non
     h_out = [bgr.RolloutResult(torch.empty((E, abi.N_METRICS), dtype=torch.float32).pin_memory().numpy(),
                                torch.empty((E, abi.N_STATUS), dtype=torch.int32).pin_memory().numpy(), None,
                                torch.empty(abi.N_AGG, dtype=torch.float64).pin_memory().numpy()) for _ in range(2)]
-    for i in range(min(warmup, 2)):
-        bgr.rollout(track, cfg, np_params[i % n_sets], np_init[i % n_sets], aggregate=True, out=h_out[i % 2])
+    # warm-up through the SAME asynchronous path: four calls walk the library's ring of three device buffer slots (each
+    # slot is ~200 MB of cudaMalloc the first time it is used) and create the four completion streams of this thread, so
+    # that no allocation or stream creation falls into the timed region (seen once on a 4-GPU box: a timed loop of 10
+    # steps took twice its time on one rank, the synchronous loop after it did not)
+    for i in range(4):
+        bgr.rollout_async(track, cfg, np_params[i % n_sets], np_init[i % n_sets], aggregate=True, out=h_out[i % 2]).wait()
     ctx.barrier()
     e2e_steps = 0.0
     w0 = time.perf_counter()
@@ -669,7 +673,7 @@ def run_skidpad_mc(ctx, episodes, sim_steps, steps, warmup):
     h_groups = [(j[0], j[4], j[5]) for j in jobs]
     e2e_value = sync_value = None
     if not serial:
-        for i in range(3):      # (the lane threads build their copy / compute pipelines and buffer rings on first use)
+        for i in range(4):      # (the lane threads build their copy / compute pipelines, buffer rings and streams on first use)
             bgr.rollout_groups_async(track, h_groups, aggregate=True, outs=h_sets[i % 2], order=[2, 1, 0]).wait()
         ctx.barrier()
         w0 = time.perf_counter()
