@@ -195,3 +195,43 @@ def test_product_never_imports_the_oracle():
                     "oracle/loop.py", "").replace("oracle/philox.py", ""), f
     code = "import sys, bgr_pathplanning_control_b200; assert not [m for m in sys.modules if m.split('.')[0] == 'oracle']"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_streaming_groups_keep_group_order_and_their_own_host_threads(monkeypatch):
+    """engine.rollout_groups_async (host logic only, no GPU): group g is always queued from lane thread g -- the
+    library's copy / compute pipeline is per host thread -- in the requested launch order; ``wait()`` answers in the
+    order the groups were given and is idempotent."""
+    import threading
+    import time
+    from bgr_pathplanning_control_b200 import engine
+
+    calls = []
+
+    class Pending:
+        def __init__(self, tag):
+            self.tag, self.waits = tag, 0
+
+        def wait(self):
+            self.waits += 1
+            return self.tag
+
+    def fake_async(track, cfg, params, init, *, aggregate=False, out=None):
+        calls.append((cfg, threading.current_thread().name, aggregate, out))
+        time.sleep(0.01)
+        return Pending((cfg, params, init))
+
+    monkeypatch.setattr(engine, "rollout_async", fake_async)
+    groups = [("pp", 1, 2), ("st_pid", 3, 4), ("st_lqg", 5, 6)]
+    outs = ["o0", "o1", "o2"]
+    seen = {}
+    for batch in range(3):
+        pend = bgr.rollout_groups_async("track", groups, aggregate=True, outs=outs, order=[2, 1, 0])
+        assert pend.wait() == [("pp", 1, 2), ("st_pid", 3, 4), ("st_lqg", 5, 6)]
+        assert pend.wait() is pend.wait()
+        for cfg, thread, aggregate, out in calls[-3:]:
+            assert aggregate is True and out == outs[[g[0] for g in groups].index(cfg)]
+            assert seen.setdefault(cfg, thread) == thread          # the same lane thread in every batch
+    assert len(set(seen.values())) == 3                            # one thread per group
+    assert len(calls) == 9
+    with pytest.raises(IndexError):
+        bgr.rollout_groups_async("track", groups, order=[3])
