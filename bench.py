@@ -482,14 +482,18 @@ def run_rollout_workload(ctx, workload, E, S, steps, warmup, *, strong_total=Non
     e2e_steps = 0.0
     w0 = time.perf_counter()
     pending = None
+    marks = [w0]                                                          # host clock when each step's result was read
     for i in range(steps):
         nxt = bgr.rollout_async(track, cfg, np_params[i % n_sets], np_init[i % n_sets], aggregate=True, out=h_out[i % 2])
         if pending is not None:
             e2e_steps += float(pending.wait().aggregate[abi.A_STEPS])     # the result of step i - 1 is read on the host
+            marks.append(time.perf_counter())
         pending = nxt
     e2e_steps += float(pending.wait().aggregate[abi.A_STEPS])
+    marks.append(time.perf_counter())
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - w0) * 1e3
+    e2e_step_ms = [round((b - a) * 1e3, 3) for a, b in zip(marks[:-1], marks[1:])]
     # the same call, one step at a time (upload, run, download, synchronise; nothing in flight across steps)
     w1 = time.perf_counter()
     sync_steps = 0.0
@@ -501,6 +505,7 @@ def run_rollout_workload(ctx, workload, E, S, steps, warmup, *, strong_total=Non
         ctx.dist.barrier()
     e2e_value = ctx.reduce(e2e_steps, "SUM") / (ctx.reduce(e2e_ms, "MAX") * 1e-3)
     sync_value = ctx.reduce(sync_steps, "SUM") / (ctx.reduce(sync_ms, "MAX") * 1e-3)
+    e2e_slowest_ms = ctx.reduce(max(e2e_step_ms), "MAX")         # a one-off stall on ANY rank shows here
     d2h = E * (abi.N_METRICS * 4 + abi.N_STATUS * 4) + abi.N_AGG * 8
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -548,6 +553,9 @@ def run_rollout_workload(ctx, workload, E, S, steps, warmup, *, strong_total=Non
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "bgr_rollout_host_async (pinned numpy in, numpy out; step i + 1 queued before step i is read)",
                 "frac_of_value": e2e_value / value,
+                # result-to-result intervals on rank 0's host clock (the first one includes filling the pipeline), and the
+                # longest interval any rank saw: a one-off host or driver stall is visible instead of silently averaged in
+                "step_ms": e2e_step_ms, "slowest_step_ms_any_rank": e2e_slowest_ms,
                 "one_call_at_a_time": {"value": sync_value, "api": "bgr_rollout_host", "frac_of_value": sync_value / value}},
         "gpu_launches": int(launches),
         "roofline": roof,
