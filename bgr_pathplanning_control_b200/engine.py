@@ -475,12 +475,23 @@ class PendingGroups:
     order the groups were given) once every group's result arrays are filled."""
 
     def __init__(self, futures):
-        self._futures, self._results = futures, None
+        self._futures, self._results, self._error = futures, None, None
 
     def wait(self):
-        if self._results is None:
-            self._results = [f.result().wait() for f in self._futures]
-            self._futures = None
+        if self._futures is not None:
+            # every group is waited for even when one of them failed: the caller's arrays must not be in flight any
+            # more when the error surfaces (the first error is raised once all groups have settled, and again on
+            # every later wait())
+            results = []
+            for f in self._futures:
+                try:
+                    results.append(f.result().wait())
+                except Exception as exc:      # noqa: BLE001
+                    results.append(None)
+                    self._error = self._error or exc
+            self._futures, self._results = None, results
+        if self._error is not None:
+            raise self._error
         return self._results
 
 

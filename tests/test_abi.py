@@ -235,3 +235,23 @@ def test_streaming_groups_keep_group_order_and_their_own_host_threads(monkeypatc
     assert len(calls) == 9
     with pytest.raises(IndexError):
         bgr.rollout_groups_async("track", groups, order=[3])
+
+    # one group fails: the others are still waited for (their arrays must not stay in flight), then the error surfaces
+    waited = []
+
+    class Slow(Pending):
+        def wait(self):
+            waited.append(self.tag[0])
+            return super().wait()
+
+    def failing_async(track, cfg, params, init, *, aggregate=False, out=None):
+        if cfg == "st_pid":
+            raise RuntimeError("boom")
+        return Slow((cfg, params, init))
+
+    monkeypatch.setattr(engine, "rollout_async", failing_async)
+    pend = bgr.rollout_groups_async("track", groups)
+    for _ in range(2):
+        with pytest.raises(RuntimeError, match="boom"):
+            pend.wait()
+    assert waited == ["pp", "st_lqg"]
